@@ -1,0 +1,248 @@
+// fa_api.cu — host layer behind the C ABI of include/fa_b200.h.
+//
+// Replaces the reference's host launch / dispatch level:
+//   code/cuda_fa1/main.cu:377-385 (grid/block/shmem math + raw <<<>>> launch)
+//   code/cutlass_cuda_fa1/run/flash_attn_cutlass.cu:457-544 (templated launcher + head_dim switch)
+//   code/cutlass_cuda_fa1/run/flash_attn_unified.cu:545-617
+// Validates arguments, encodes the four TMA tensor maps, picks the kernel instantiation and
+// enqueues it.  Allocates nothing, never synchronises, returns a status code.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/fa_b200.h"
+#include "fa_fwd_sm100.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  if (getenv("FA_B200_VERBOSE")) fprintf(stderr, "fa_b200: %s\n", g_err);
+  return code;
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// [BH, rows, d] tensor, d contiguous, viewed as a 3-D TMA tensor {d, rows, BH}; box = 64 x 128 x 1
+// with the 128-byte swizzle the UMMA descriptors expect.  Out-of-range rows read as zero and are
+// clipped on store, which is what makes ragged N work.
+int make_tmap(CUtensorMap* tm, const void* base, int dtype, int d, int rows, long long bh,
+              long long stride_bh_elems) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, (cuuint64_t)bh};
+  cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)stride_bh_elems * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, dtype == FA_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return FA_B200_OK;
+}
+
+int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  static std::atomic<int> cc_cache[64];
+  int cc = (dev < 64) ? cc_cache[dev].load() : 0;
+  if (cc == 0) {
+    int major = 0, minor = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    cc = major * 10 + minor;
+    if (dev < 64) cc_cache[dev].store(cc);
+  }
+  if (cc / 10 != 10)
+    return fail(FA_B200_ERR_ARCH, "device %d is sm_%d; this library only runs on sm_100 (B200) and has no fallback",
+                dev, cc);
+  return FA_B200_OK;
+}
+
+template <int D, bool kBF16, bool kCausal>
+int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+           const fa::FwdArgs& args, long long grid, cudaStream_t stream) {
+  auto kern = fa::fa_fwd_sm100_kernel<D, kBF16, kCausal>;
+  constexpr int smem = fa::FwdTraits<D>::kSmemBytes;
+  // opt-in to > 48 KB dynamic shared memory: once per device per instantiation
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load() & bit)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+    configured.fetch_or(bit);
+  }
+  kern<<<dim3((unsigned)grid), dim3(fa::kNumThreads), smem, stream>>>(tq, tk, tv, to, args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return FA_B200_OK;
+}
+
+unsigned long long env_u64(const char* name, unsigned long long dflt) {
+  const char* s = getenv(name);
+  return s ? strtoull(s, nullptr, 0) : dflt;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fa_b200_forward(const fa_b200_params* p) {
+  if (!p) return fail(FA_B200_ERR_NULL, "params is NULL");
+  if (!p->Q || !p->K || !p->V || !p->O) return fail(FA_B200_ERR_NULL, "Q, K, V and O must be non-NULL");
+  if (p->B <= 0 || p->H <= 0 || p->N <= 0 || p->N_kv < 0)
+    return fail(FA_B200_ERR_SHAPE, "bad shape B=%d H=%d N=%d N_kv=%d", p->B, p->H, p->N, p->N_kv);
+  if (p->d != 64 && p->d != 128)
+    return fail(FA_B200_ERR_HEAD_DIM, "unsupported head_dim=%d (supported: 64, 128)", p->d);
+  if (p->dtype != FA_B200_FP16 && p->dtype != FA_B200_BF16)
+    return fail(FA_B200_ERR_DTYPE, "unsupported dtype=%d (0 = fp16, 1 = bf16)", p->dtype);
+  const long long BH = (long long)p->B * p->H;
+  const int Nq = p->N, Nkv = p->N_kv ? p->N_kv : p->N;
+  const int d = p->d;
+  const long long num_q_blocks = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
+  if (BH * num_q_blocks > 0x7fffffffLL) return fail(FA_B200_ERR_SHAPE, "B*H*ceil(N/256) exceeds the grid limit");
+  const long long qs = p->q_stride_bh ? p->q_stride_bh : (long long)Nq * d;
+  const long long ks = p->kv_stride_bh ? p->kv_stride_bh : (long long)Nkv * d;
+  const long long os = p->o_stride_bh ? p->o_stride_bh : (long long)Nq * d;
+  const long long ss = p->stat_stride_bh ? p->stat_stride_bh : (long long)Nq;
+  auto mis = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+  if (mis(p->Q) || mis(p->K) || mis(p->V) || mis(p->O))
+    return fail(FA_B200_ERR_ALIGNMENT, "Q, K, V, O base pointers must be 16-byte aligned");
+  if ((qs % 8) || (ks % 8) || (os % 8))
+    return fail(FA_B200_ERR_ALIGNMENT, "(b,h) strides must be multiples of 8 elements");
+  if (qs < (long long)Nq * d || ks < (long long)Nkv * d || os < (long long)Nq * d || ss < Nq)
+    return fail(FA_B200_ERR_SHAPE, "(b,h) stride smaller than one slice");
+  int rc = check_device();
+  if (rc) return rc;
+
+  CUtensorMap tq, tk, tv, to;
+  if ((rc = make_tmap(&tq, p->Q, p->dtype, d, Nq, BH, qs))) return rc;
+  if ((rc = make_tmap(&tk, p->K, p->dtype, d, Nkv, BH, ks))) return rc;
+  if ((rc = make_tmap(&tv, p->V, p->dtype, d, Nkv, BH, ks))) return rc;
+  if ((rc = make_tmap(&to, p->O, p->dtype, d, Nq, BH, os))) return rc;
+
+  const float scale = (p->softmax_scale != 0.f) ? p->softmax_scale : 1.0f / sqrtf((float)d);
+  fa::FwdArgs a{};
+  a.lse = p->lse;
+  a.l = p->l;
+  a.m = p->m;
+  a.Nq = Nq;
+  a.Nkv = Nkv;
+  a.causal_off = Nkv - Nq;
+  a.num_q_blocks = (int)num_q_blocks;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.stat_stride_bh = ss;
+  const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;
+  // Q, K: K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.
+  a.desc_hi_qk = fa::umma_desc_hi_bits(16, 1024, 2);
+  // V: MN-major (d contiguous), 128B swizzle: 64-column halves one box (16 KB) apart (LBO),
+  // 8-key groups 1024 B apart (SBO).
+  a.desc_hi_v = fa::umma_desc_hi_bits(fa::FwdTraits<128>::kBoxBytes, 1024, 2);
+  a.idesc_qk = fa::umma_idesc(fmt, 0, 0, 128, 128);
+  a.idesc_pv = fa::umma_idesc(fmt, 0, 1, 128, (unsigned)d);
+  // bring-up overrides (debug only)
+  a.desc_hi_qk = env_u64("FA_B200_DESC_HI_QK", a.desc_hi_qk);
+  a.desc_hi_v = env_u64("FA_B200_DESC_HI_V", a.desc_hi_v);
+  a.idesc_qk = (unsigned)env_u64("FA_B200_IDESC_QK", a.idesc_qk);
+  a.idesc_pv = (unsigned)env_u64("FA_B200_IDESC_PV", a.idesc_pv);
+
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
+  const long long grid = BH * num_q_blocks;
+  const bool bf16 = p->dtype == FA_B200_BF16;
+  const bool causal = p->causal != 0;
+#define FA_LAUNCH(D_, BF_, C_) return launch<D_, BF_, C_>(tq, tk, tv, to, a, grid, stream)
+  if (d == 128) {
+    if (bf16) { if (causal) FA_LAUNCH(128, true, true); else FA_LAUNCH(128, true, false); }
+    else      { if (causal) FA_LAUNCH(128, false, true); else FA_LAUNCH(128, false, false); }
+  } else {
+    if (bf16) { if (causal) FA_LAUNCH(64, true, true); else FA_LAUNCH(64, true, false); }
+    else      { if (causal) FA_LAUNCH(64, false, true); else FA_LAUNCH(64, false, false); }
+  }
+#undef FA_LAUNCH
+}
+
+int fa_b200_forward_legacy(const void* Q, const void* K, const void* V, void* O, float* l, float* m,
+                           int B, int H, int N, int d, int M, void* stream) {
+  (void)M;  // FA1 tile-size knob (flashAttention.cu:17-18); tile shape is fixed by the hardware here
+  fa_b200_params p;
+  memset(&p, 0, sizeof(p));
+  p.Q = Q; p.K = K; p.V = V; p.O = O; p.l = l; p.m = m;
+  p.B = B; p.H = H; p.N = N; p.d = d;
+  p.dtype = FA_B200_FP16;
+  p.stream = stream;
+  return fa_b200_forward(&p);
+}
+
+int fa_b200_forward_fp16(const void* Q, const void* K, const void* V, void* O, int batch_size,
+                         int num_heads, int seq_len, int head_dim, void* stream) {
+  fa_b200_params p;
+  memset(&p, 0, sizeof(p));
+  p.Q = Q; p.K = K; p.V = V; p.O = O;
+  p.B = batch_size; p.H = num_heads; p.N = seq_len; p.d = head_dim;
+  p.dtype = FA_B200_FP16;
+  p.stream = stream;
+  return fa_b200_forward(&p);
+}
+
+uint64_t fa_b200_launch_count(void) { return g_launches.load(); }
+const char* fa_b200_last_error(void) { return g_err; }
+int fa_b200_version(void) { return (FA_B200_VERSION_MAJOR << 16) | FA_B200_VERSION_MINOR; }
+
+const char* fa_b200_status_string(int s) {
+  switch (s) {
+    case FA_B200_OK: return "ok";
+    case FA_B200_ERR_NULL: return "null pointer";
+    case FA_B200_ERR_SHAPE: return "bad shape";
+    case FA_B200_ERR_HEAD_DIM: return "unsupported head_dim";
+    case FA_B200_ERR_DTYPE: return "unsupported dtype";
+    case FA_B200_ERR_ALIGNMENT: return "bad alignment";
+    case FA_B200_ERR_ARCH: return "not an sm_100 device";
+    case FA_B200_ERR_CUDA: return "CUDA error";
+    case FA_B200_ERR_DRIVER: return "driver / tensor-map error";
+    default: return "unknown status";
+  }
+}
+
+}  // extern "C"
+
+// Used by fa_merge.cu so that every kernel of the library is counted in fa_b200_launch_count().
+namespace fa {
+void count_launch() { g_launches.fetch_add(1); }
+int api_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+int api_check_device() { return check_device(); }
+}  // namespace fa

@@ -1,0 +1,146 @@
+// fa_merge.cu — logsumexp merge of attention partials for ring attention (SURVEY.md section 8e;
+// the reference has no multi-GPU path, this is new work named by BASELINE.json's north_star).
+//
+//   lse' = log(e^lse_a + e^lse_b),  O' = O_a e^(lse_a - lse') + O_b e^(lse_b - lse')
+//
+// HBM-bound element-wise kernels: one warp per row group, 16-byte vector loads/stores, grid-stride.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/fa_b200.h"
+
+namespace fa {
+void count_launch();
+int api_fail(int code, const char* msg);
+int api_check_device();
+
+template <bool kBF16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if constexpr (kBF16) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  } else {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+}
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2f(float a, float b) {
+  if constexpr (kBF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+// One thread handles 8 consecutive elements of a row (16 B of the 16-bit partial, 32 B of fp32).
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+merge_partial_kernel(float* __restrict__ O_acc, float* __restrict__ lse_acc,
+                     const uint4* __restrict__ O_part, const float* __restrict__ lse_part,
+                     long long rows, int d) {
+  const int vec_per_row = d / 8;
+  const long long total = rows * vec_per_row;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / vec_per_row;
+    const int v = (int)(idx - row * vec_per_row);
+    const float la = lse_acc[row], lb = lse_part[row];
+    if (lb == -INFINITY) continue;            // nothing to add for this row
+    const float mx = fmaxf(la, lb);
+    const float ea = (la == -INFINITY) ? 0.f : __expf(la - mx);
+    const float eb = __expf(lb - mx);
+    const float inv = 1.f / (ea + eb);
+    const float wa = ea * inv, wb = eb * inv;
+    const uint4 pv = O_part[idx];
+    float4* acc = reinterpret_cast<float4*>(O_acc + row * d + v * 8);
+    float4 a0 = acc[0], a1 = acc[1];
+    const float2 p0 = unpack2<kBF16>(pv.x), p1 = unpack2<kBF16>(pv.y), p2 = unpack2<kBF16>(pv.z),
+                 p3 = unpack2<kBF16>(pv.w);
+    a0.x = a0.x * wa + p0.x * wb; a0.y = a0.y * wa + p0.y * wb;
+    a0.z = a0.z * wa + p1.x * wb; a0.w = a0.w * wa + p1.y * wb;
+    a1.x = a1.x * wa + p2.x * wb; a1.y = a1.y * wa + p2.y * wb;
+    a1.z = a1.z * wa + p3.x * wb; a1.w = a1.w * wa + p3.y * wb;
+    acc[0] = a0; acc[1] = a1;
+  }
+}
+
+// lse_acc update runs after every thread of the merge has read the old value: separate tiny kernel.
+__global__ void __launch_bounds__(256)
+merge_lse_kernel(float* __restrict__ lse_acc, const float* __restrict__ lse_part, long long rows) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const float la = lse_acc[r], lb = lse_part[r];
+    if (lb == -INFINITY) continue;
+    const float mx = fmaxf(la, lb);
+    const float ea = (la == -INFINITY) ? 0.f : __expf(la - mx);
+    lse_acc[r] = mx + __logf(ea + __expf(lb - mx));
+  }
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+cast_output_kernel(uint4* __restrict__ O, const float4* __restrict__ O_acc, long long nvec) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < nvec;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const float4 a0 = O_acc[2 * idx], a1 = O_acc[2 * idx + 1];
+    uint4 o;
+    o.x = pack2f<kBF16>(a0.x, a0.y); o.y = pack2f<kBF16>(a0.z, a0.w);
+    o.z = pack2f<kBF16>(a1.x, a1.y); o.w = pack2f<kBF16>(a1.z, a1.w);
+    O[idx] = o;
+  }
+}
+
+inline unsigned grid_for(long long work_items) {
+  long long blocks = (work_items + 255) / 256;
+  const long long cap = 148LL * 8;   // 8 resident 256-thread CTAs per SM, 148 SMs
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+}  // namespace fa
+
+extern "C" int fa_b200_merge_partial(float* O_acc, float* lse_acc, const void* O_part, const float* lse_part,
+                                     int64_t rows, int d, int dtype, void* stream) {
+  if (!O_acc || !lse_acc || !O_part || !lse_part) return fa::api_fail(FA_B200_ERR_NULL, "merge: NULL pointer");
+  if (rows <= 0 || d <= 0 || d % 8) return fa::api_fail(FA_B200_ERR_SHAPE, "merge: rows > 0 and d % 8 == 0 required");
+  if (dtype != FA_B200_FP16 && dtype != FA_B200_BF16) return fa::api_fail(FA_B200_ERR_DTYPE, "merge: bad dtype");
+  if ((reinterpret_cast<uintptr_t>(O_acc) | reinterpret_cast<uintptr_t>(O_part)) & 15)
+    return fa::api_fail(FA_B200_ERR_ALIGNMENT, "merge: O_acc and O_part must be 16-byte aligned");
+  int rc = fa::api_check_device();
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = rows * (d / 8);
+  if (dtype == FA_B200_BF16)
+    fa::merge_partial_kernel<true><<<fa::grid_for(total), 256, 0, s>>>(O_acc, lse_acc, (const uint4*)O_part, lse_part, rows, d);
+  else
+    fa::merge_partial_kernel<false><<<fa::grid_for(total), 256, 0, s>>>(O_acc, lse_acc, (const uint4*)O_part, lse_part, rows, d);
+  fa::merge_lse_kernel<<<fa::grid_for(rows), 256, 0, s>>>(lse_acc, lse_part, rows);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fa::api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
+  fa::count_launch(); fa::count_launch();
+  return FA_B200_OK;
+}
+
+extern "C" int fa_b200_cast_output(void* O, const float* O_acc, int64_t rows, int d, int dtype, void* stream) {
+  if (!O || !O_acc) return fa::api_fail(FA_B200_ERR_NULL, "cast: NULL pointer");
+  if (rows <= 0 || d <= 0 || d % 8) return fa::api_fail(FA_B200_ERR_SHAPE, "cast: rows > 0 and d % 8 == 0 required");
+  if (dtype != FA_B200_FP16 && dtype != FA_B200_BF16) return fa::api_fail(FA_B200_ERR_DTYPE, "cast: bad dtype");
+  if ((reinterpret_cast<uintptr_t>(O_acc) | reinterpret_cast<uintptr_t>(O)) & 15)
+    return fa::api_fail(FA_B200_ERR_ALIGNMENT, "cast: O and O_acc must be 16-byte aligned");
+  int rc = fa::api_check_device();
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long nvec = rows * (d / 8);
+  if (dtype == FA_B200_BF16)
+    fa::cast_output_kernel<true><<<fa::grid_for(nvec), 256, 0, s>>>((uint4*)O, (const float4*)O_acc, nvec);
+  else
+    fa::cast_output_kernel<false><<<fa::grid_for(nvec), 256, 0, s>>>((uint4*)O, (const float4*)O_acc, nvec);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fa::api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
+  fa::count_launch();
+  return FA_B200_OK;
+}

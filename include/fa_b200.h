@@ -1,0 +1,123 @@
+/*
+ * fa_b200.h — C ABI of the B200 (sm_100a) FlashAttention forward library (libfa_b200.so).
+ *
+ * This is the drop-in boundary for the CUDA launch path of santiweide/flash-attention-impls.
+ * Every entry point takes plain device pointers and sizes; nothing here depends on torch,
+ * CUTLASS or C++.  Tensors are the reference's layout: contiguous row-major [B, H, N, d]
+ * (reference: code/cuda_fa1/flashAttention.cu:30, offset ((b*H+h)*N)*d) and per-row
+ * statistics [B, H, N] fp32 (flashAttention.cu:31).
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   - code/cuda_fa1/flashAttention.h:8-11   __global__ flash_attention_forward(Q,K,V,O,l,m,B,H,N,d,M)
+ *     and its raw <<<grid,block,shmem>>> call sites code/cuda_fa1/main.cu:297-303, :444
+ *       -> fa_b200_forward_legacy()
+ *   - code/cutlass_cuda_fa1/run/flash_attn_cutlass.cu:519-544  flash_attention_cutlass_dispatch
+ *   - code/cutlass_cuda_fa1/run/flash_attn_unified.cu:545-617  flash_attention_forward_dispatch,
+ *     flash_attention_small_tile_dispatch, attention_reference_dispatch
+ *       -> fa_b200_forward_fp16()  (same argument list; the C++-linkage shims with the reference's
+ *          exact names live in flash_attention_impls_b200/csrc/fa_ref_shims.cu)
+ *   - code/triton_fa2/FA2-triton.py:173-205,240-244  flash_attention(q,k,v,causal) -> (o, m, l)
+ *       -> fa_b200_forward() with causal=1 and the l/m/lse outputs
+ *
+ * All calls are enqueue-only on `stream`, allocate nothing, never synchronise, never exit(),
+ * and are safe to call from several host threads (one per GPU).  There is NO CPU fallback: on a
+ * device that is not sm_100 the calls return FA_B200_ERR_ARCH.
+ */
+#ifndef FA_B200_H_
+#define FA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_B200_VERSION_MAJOR 0
+#define FA_B200_VERSION_MINOR 1
+
+/* status codes (0 = ok).  The reference returns void and prints to stderr
+ * (flash_attn_cutlass.cu:540-542, :510-514); the C ABI returns codes instead. */
+enum fa_b200_status {
+  FA_B200_OK = 0,
+  FA_B200_ERR_NULL = 1,        /* a required pointer is NULL */
+  FA_B200_ERR_SHAPE = 2,       /* B,H,N <= 0, N_kv < 0, B*H too large */
+  FA_B200_ERR_HEAD_DIM = 3,    /* d not in {64,128} (reference supports {32,64,128}) */
+  FA_B200_ERR_DTYPE = 4,       /* dtype not FA_B200_FP16 / FA_B200_BF16 */
+  FA_B200_ERR_ALIGNMENT = 5,   /* base pointers must be 16-byte aligned, strides multiples of 8 elements */
+  FA_B200_ERR_ARCH = 6,        /* current device is not compute capability 10.x */
+  FA_B200_ERR_CUDA = 7,        /* a CUDA runtime/driver call failed; see fa_b200_last_error() */
+  FA_B200_ERR_DRIVER = 8       /* cuTensorMapEncodeTiled unavailable or failed */
+};
+
+enum fa_b200_dtype {
+  FA_B200_FP16 = 0,            /* __half, the reference's dtype (flashAttention.h:8-11) */
+  FA_B200_BF16 = 1             /* __nv_bfloat16 (new; BASELINE configs c3-c5) */
+};
+
+/* Full parameter block.  Zero-initialise, then fill.  Fields the reference has no notion of
+ * (N_kv, strides, causal, lse) default to the reference behaviour when left 0 / NULL. */
+typedef struct fa_b200_params {
+  const void* Q;     /* [B,H,N,d]    dtype */
+  const void* K;     /* [B,H,N_kv,d] dtype */
+  const void* V;     /* [B,H,N_kv,d] dtype */
+  void* O;           /* [B,H,N,d]    dtype */
+  float* lse;        /* optional [B,H,N]: natural-log logsumexp of the scaled scores, = m + ln(l) */
+  float* l;          /* optional [B,H,N]: sum_j exp(s_ij - m_i)    (flashAttention.cu:115-120,137) */
+  float* m;          /* optional [B,H,N]: max_j s_ij, s = q.k*scale (flashAttention.cu:138)        */
+  int B, H, N, d;
+  int N_kv;          /* 0 => N (self-attention, the only case the reference has) */
+  int dtype;         /* enum fa_b200_dtype */
+  int causal;        /* 0 / 1.  Mask rule col > row + (N_kv - N) -> -inf; with N_kv == N this is
+                        FA2-triton.py:70-73 (square, top-left aligned) */
+  float softmax_scale; /* 0 => 1/sqrt(d) (flashAttention.cu:96, flash_attn_cutlass.cu:470) */
+  /* Element strides between consecutive (b*H+h) slices; 0 => dense (N*d, N_kv*d, N*d, N).
+   * Rows are always d-contiguous.  Lets a caller pass row sub-ranges of a longer sequence
+   * (used by the ring-attention driver). */
+  int64_t q_stride_bh, kv_stride_bh, o_stride_bh, stat_stride_bh;
+  void* stream;      /* cudaStream_t; NULL => legacy default stream, as in the reference */
+} fa_b200_params;
+
+/* Primary entry point. */
+int fa_b200_forward(const fa_b200_params* p);
+
+/* Same argument list as the reference kernel flash_attention_forward (flashAttention.h:8-11)
+ * plus the stream; call this where the reference does `flash_attention_forward<<<grid,block,
+ * shmem>>>(Q,K,V,O,l,m,B,H,N,d,M)`.  fp16, non-causal.  M (the FA1 "SRAM size" knob that picks
+ * Bc/Br, flashAttention.cu:17-18) is accepted and ignored.  l and m get the reference's meaning. */
+int fa_b200_forward_legacy(const void* Q, const void* K, const void* V, void* O,
+                           float* l, float* m, int B, int H, int N, int d, int M,
+                           void* stream);
+
+/* Same argument list as flash_attention_cutlass_dispatch (flash_attn_cutlass.cu:519-529) and the
+ * three dispatchers of flash_attn_unified.cu:545-617.  fp16, non-causal, O only. */
+int fa_b200_forward_fp16(const void* Q, const void* K, const void* V, void* O,
+                         int batch_size, int num_heads, int seq_len, int head_dim,
+                         void* stream);
+
+/* Merge two attention partials over disjoint key sets (ring attention):
+ *   lse' = log(exp(lse_acc) + exp(lse_part));  O_acc' = O_acc*exp(lse_acc-lse') + O_part*exp(lse_part-lse')
+ * O_acc is fp32 [rows, d] (row stride d), O_part is dtype [rows, d]; lse_* are fp32 [rows].
+ * Rows whose lse_part is -inf are left unchanged.  In place on (O_acc, lse_acc). */
+int fa_b200_merge_partial(float* O_acc, float* lse_acc, const void* O_part, const float* lse_part,
+                          int64_t rows, int d, int dtype, void* stream);
+
+/* Final cast of the fp32 ring accumulator to dtype: O[rows,d] = (dtype) O_acc[rows,d]. */
+int fa_b200_cast_output(void* O, const float* O_acc, int64_t rows, int d, int dtype, void* stream);
+
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+uint64_t fa_b200_launch_count(void);
+
+/* Message for the last non-OK status returned on the calling thread ("" if none). */
+const char* fa_b200_last_error(void);
+
+/* Human-readable name of a status code. */
+const char* fa_b200_status_string(int status);
+
+/* (major << 16) | minor */
+int fa_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H_ */

@@ -1,0 +1,434 @@
+// tools/fa_selftest.cu — standalone bring-up / parity binary (no torch): runs the library through its
+// C ABI on seeded inputs and checks it against the CPU oracle (oracle/liboracle.so), and unit-tests
+// the UMMA shared-memory / instruction descriptors with a single-CTA GEMM pair.
+//
+//   fa_selftest attn B H N d dtype(0=fp16,1=bf16) causal [N_kv] [set(R|S)] [iters]
+//   fa_selftest umma D [lbo_v sbo_v kstep_v_bytes lbo_qk sbo_qk]
+//   fa_selftest ref  B H N d M            (reference FA1 kernel from oracle/_ref vs library, fp16)
+//
+// Test infrastructure only: the oracle is the checker here, never the thing measured.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../flash_attention_impls_b200/csrc/sm100_ptx.cuh"
+#include "../include/fa_b200.h"
+
+extern "C" {
+int oracle_attention_f32(const float*, const float*, const float*, float*, float*, float*, float*, int, int, int,
+                         int, int, float, int, int, int);
+float oracle_max_symmetric_rel_err(const float*, const float*, size_t);
+void fixture_reference_stream(float*, size_t, float, float);
+void fixture_normal_bf16(float*, size_t, uint32_t, float);
+void fixture_uniform_bf16(float*, size_t, uint32_t, float, float);
+}
+
+#define CK(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess) {                                                               \
+      fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(3);                                                                             \
+    }                                                                                      \
+  } while (0)
+
+static std::vector<uint16_t> to16(const std::vector<float>& x, bool bf16) {
+  std::vector<uint16_t> o(x.size());
+  for (size_t i = 0; i < x.size(); ++i) {
+    if (bf16) {
+      __nv_bfloat16 v = __float2bfloat16(x[i]);
+      memcpy(&o[i], &v, 2);
+    } else {
+      __half v = __float2half(x[i]);
+      memcpy(&o[i], &v, 2);
+    }
+  }
+  return o;
+}
+static float from16(uint16_t u, bool bf16) {
+  if (bf16) {
+    __nv_bfloat16 v;
+    memcpy(&v, &u, 2);
+    return __bfloat162float(v);
+  }
+  __half v;
+  memcpy(&v, &u, 2);
+  return __half2float(v);
+}
+
+// ------------------------------------------------------------------------------------------ attn
+static int run_attn(int argc, char** argv) {
+  if (argc < 8) {
+    fprintf(stderr, "usage: attn B H N d dtype causal [N_kv] [set] [iters]\n");
+    return 2;
+  }
+  const int B = atoi(argv[2]), H = atoi(argv[3]), N = atoi(argv[4]), d = atoi(argv[5]);
+  const int dtype = atoi(argv[6]), causal = atoi(argv[7]);
+  const int Nkv = (argc > 8 && atoi(argv[8]) > 0) ? atoi(argv[8]) : N;
+  const char set = (argc > 9) ? argv[9][0] : 'S';
+  const int iters = (argc > 10) ? atoi(argv[10]) : 0;
+  const bool bf16 = dtype == 1;
+  const int BH = B * H;
+  const size_t nq = (size_t)BH * N * d, nk = (size_t)BH * Nkv * d, ns = (size_t)BH * N;
+
+  std::vector<float> q(nq), k(nk), v(nk);
+  if (set == 'R') {
+    fixture_reference_stream(q.data(), nq, 0.f, 0.02f);
+    fixture_reference_stream(k.data(), nk, 0.f, 0.02f);
+    fixture_reference_stream(v.data(), nk, 0.f, 0.02f);
+  } else {
+    fixture_normal_bf16(q.data(), nq, 1, 1.f);
+    fixture_normal_bf16(k.data(), nk, 2, 1.f);
+    fixture_uniform_bf16(v.data(), nk, 3, -0.5f, 0.5f);
+  }
+  auto q16 = to16(q, bf16), k16 = to16(k, bf16), v16 = to16(v, bf16);
+  // the oracle sees exactly the 16-bit-rounded reals
+  for (size_t i = 0; i < nq; ++i) q[i] = from16(q16[i], bf16);
+  for (size_t i = 0; i < nk; ++i) { k[i] = from16(k16[i], bf16); v[i] = from16(v16[i], bf16); }
+
+  void *dQ, *dK, *dV, *dO;
+  float *dlse, *dl, *dm;
+  CK(cudaMalloc(&dQ, nq * 2)); CK(cudaMalloc(&dK, nk * 2)); CK(cudaMalloc(&dV, nk * 2)); CK(cudaMalloc(&dO, nq * 2));
+  CK(cudaMalloc(&dlse, ns * 4)); CK(cudaMalloc(&dl, ns * 4)); CK(cudaMalloc(&dm, ns * 4));
+  CK(cudaMemcpy(dQ, q16.data(), nq * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dK, k16.data(), nk * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dV, v16.data(), nk * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dO, 0xff, nq * 2));
+  CK(cudaMemset(dlse, 0xff, ns * 4));
+
+  fa_b200_params p;
+  memset(&p, 0, sizeof(p));
+  p.Q = dQ; p.K = dK; p.V = dV; p.O = dO; p.lse = dlse; p.l = dl; p.m = dm;
+  p.B = B; p.H = H; p.N = N; p.d = d; p.N_kv = (Nkv == N) ? 0 : Nkv; p.dtype = dtype; p.causal = causal;
+  int rc = fa_b200_forward(&p);
+  if (rc) { printf("RESULT attn FAIL status=%d (%s)\n", rc, fa_b200_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("RESULT attn FAIL kernel error: %s\n", cudaGetErrorString(e)); return 1; }
+
+  std::vector<uint16_t> o16(nq);
+  std::vector<float> lse(ns), l(ns), m(ns);
+  CK(cudaMemcpy(o16.data(), dO, nq * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(lse.data(), dlse, ns * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(l.data(), dl, ns * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(m.data(), dm, ns * 4, cudaMemcpyDeviceToHost));
+
+  // oracle on a bounded number of (b,h) slices / rows
+  const double flops_full = 4.0 * BH * (double)N * Nkv * d;
+  int bh_check = BH;
+  while (bh_check > 1 && 4.0 * bh_check * (double)N * Nkv * d > 6e10) bh_check = (bh_check + 1) / 2;
+  std::vector<float> oref((size_t)bh_check * N * d), lref((size_t)bh_check * N), mref((size_t)bh_check * N),
+      lseref((size_t)bh_check * N);
+  const int nth = std::max(1u, std::thread::hardware_concurrency());
+  // check the LAST bh_check slices (exercises the bh offset arithmetic)
+  const int bh0 = BH - bh_check;
+  oracle_attention_f32(q.data() + (size_t)bh0 * N * d, k.data() + (size_t)bh0 * Nkv * d,
+                       v.data() + (size_t)bh0 * Nkv * d, oref.data(), lseref.data(), lref.data(), mref.data(),
+                       bh_check, N, Nkv, d, causal, 0.f, nth, 0, 0);
+  double max_o = 0, max_lse = 0, max_l = 0, max_m = 0;
+  size_t bad_o = 0, nan_o = 0;
+  std::vector<float> ogpu((size_t)bh_check * N * d);
+  for (size_t i = 0; i < ogpu.size(); ++i) {
+    const float g = from16(o16[(size_t)bh0 * N * d + i], bf16);
+    ogpu[i] = g;
+    if (!(g == g)) { ++nan_o; continue; }
+    const double err = fabs((double)g - oref[i]);
+    if (err > max_o) max_o = err;
+    if (err > 2e-3) ++bad_o;
+  }
+  for (size_t i = 0; i < lseref.size(); ++i) {
+    const size_t gi = (size_t)bh0 * N + i;
+    if (std::isinf(lseref[i])) { if (!(std::isinf(lse[gi]) && lse[gi] < 0)) max_lse = 1e30; continue; }
+    const double el = fabs((double)lse[gi] - lseref[i]) / std::max(1.0, (double)fabs(lseref[i]));
+    if (!(el == el) || el > max_lse) max_lse = (el == el) ? el : 1e30;
+    max_m = std::max(max_m, fabs((double)m[gi] - mref[i]));
+    max_l = std::max(max_l, fabs((double)l[gi] - lref[i]) / std::max(1.0, (double)fabs(lref[i])));
+  }
+  const float sym = oracle_max_symmetric_rel_err(ogpu.data(), oref.data(), ogpu.size());
+  const bool pass = nan_o == 0 && max_o <= 2e-3 && max_lse <= 1e-4;
+  printf("RESULT attn %s B=%d H=%d N=%d Nkv=%d d=%d %s causal=%d set=%c checked_bh=%d  O_maxabs=%.3e (bad=%zu nan=%zu) "
+         "lse_rel=%.3e m_abs=%.3e l_rel=%.3e sym_rel=%.4f\n",
+         pass ? "PASS" : "FAIL", B, H, N, Nkv, d, bf16 ? "bf16" : "fp16", causal, set, bh_check, max_o, bad_o,
+         nan_o, max_lse, max_m, max_l, sym);
+  if (!pass) {
+    // print a few rows to help localise the bug
+    for (int r : {0, 1, 127, 128, N - 1}) {
+      if (r >= N) continue;
+      printf("  row %d: gpu O[0..3]=%.5f %.5f %.5f %.5f ref=%.5f %.5f %.5f %.5f | gpu O[64..65]=%.5f %.5f ref=%.5f %.5f | lse %.5f ref %.5f\n",
+             r, ogpu[(size_t)r * d], ogpu[(size_t)r * d + 1], ogpu[(size_t)r * d + 2], ogpu[(size_t)r * d + 3],
+             oref[(size_t)r * d], oref[(size_t)r * d + 1], oref[(size_t)r * d + 2], oref[(size_t)r * d + 3],
+             d > 64 ? ogpu[(size_t)r * d + 64] : 0.f, d > 64 ? ogpu[(size_t)r * d + 65] : 0.f,
+             d > 64 ? oref[(size_t)r * d + 64] : 0.f, d > 64 ? oref[(size_t)r * d + 65] : 0.f,
+             lse[(size_t)bh0 * N + r], lseref[r]);
+    }
+  }
+  if (iters > 0) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) fa_b200_forward(&p);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> ts;
+    for (int i = 0; i < iters; ++i) {
+      cudaEventRecord(e0);
+      fa_b200_forward(&p);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      ts.push_back(ms);
+    }
+    std::sort(ts.begin(), ts.end());
+    const double fl = causal ? flops_full * 0.5 : flops_full;
+    printf("TIMING attn B=%d H=%d N=%d d=%d %s causal=%d: median %.4f ms  min %.4f ms  -> %.1f TFLOP/s median, %.1f best\n",
+           B, H, N, d, bf16 ? "bf16" : "fp16", causal, ts[ts.size() / 2], ts[0], fl / ts[ts.size() / 2] * 1e-9,
+           fl / ts[0] * 1e-9);
+  }
+  return pass ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------ ref
+static int run_ref(int argc, char** argv) {
+  if (argc < 7) { fprintf(stderr, "usage: ref B H N d M [iters]\n"); return 2; }
+  const int B = atoi(argv[2]), H = atoi(argv[3]), N = atoi(argv[4]), d = atoi(argv[5]), M = atoi(argv[6]);
+  const int iters = argc > 7 ? atoi(argv[7]) : 0;
+  std::string dir = argv[0];
+  dir = dir.substr(0, dir.find_last_of('/'));
+  void* h = dlopen((dir + "/../oracle/_ref/libref_fa1.so").c_str(), RTLD_NOW);
+  if (!h) { printf("RESULT ref SKIP (oracle/_ref/libref_fa1.so not built: %s)\n", dlerror()); return 0; }
+  using RefFn = int (*)(const void*, const void*, const void*, void*, float*, float*, int, int, int, int, int, void*);
+  RefFn ref = (RefFn)dlsym(h, "ref_fa1_forward");
+  const int BH = B * H;
+  const size_t n = (size_t)BH * N * d, ns = (size_t)BH * N;
+  for (char set : {'R', 'S'}) {
+    std::vector<float> q(n), k(n), v(n);
+    if (set == 'R') {
+      fixture_reference_stream(q.data(), n, 0.f, 0.02f); k = q; v = q;
+    } else {
+      fixture_normal_bf16(q.data(), n, 1, 1.f); fixture_normal_bf16(k.data(), n, 2, 1.f);
+      fixture_uniform_bf16(v.data(), n, 3, -0.5f, 0.5f);
+    }
+    auto q16 = to16(q, false), k16 = to16(k, false), v16 = to16(v, false);
+    void *dQ, *dK, *dV, *dO1, *dO2; float *l1, *m1, *l2, *m2;
+    CK(cudaMalloc(&dQ, n * 2)); CK(cudaMalloc(&dK, n * 2)); CK(cudaMalloc(&dV, n * 2));
+    CK(cudaMalloc(&dO1, n * 2)); CK(cudaMalloc(&dO2, n * 2));
+    CK(cudaMalloc(&l1, ns * 4)); CK(cudaMalloc(&m1, ns * 4)); CK(cudaMalloc(&l2, ns * 4)); CK(cudaMalloc(&m2, ns * 4));
+    CK(cudaMemcpy(dQ, q16.data(), n * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dK, k16.data(), n * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dV, v16.data(), n * 2, cudaMemcpyHostToDevice));
+    int r1 = ref(dQ, dK, dV, dO1, l1, m1, B, H, N, d, M, nullptr);
+    int r2 = fa_b200_forward_legacy(dQ, dK, dV, dO2, l2, m2, B, H, N, d, M, nullptr);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (r1 || r2 || e != cudaSuccess) { printf("RESULT ref FAIL launch r1=%d r2=%d %s\n", r1, r2, cudaGetErrorString(e)); return 1; }
+    std::vector<uint16_t> o1(n), o2(n);
+    std::vector<float> hl1(ns), hm1(ns), hl2(ns), hm2(ns);
+    CK(cudaMemcpy(o1.data(), dO1, n * 2, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(o2.data(), dO2, n * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hl1.data(), l1, ns * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hm1.data(), m1, ns * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hl2.data(), l2, ns * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hm2.data(), m2, ns * 4, cudaMemcpyDeviceToHost));
+    double mo = 0, mlse = 0, mm = 0, sym = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const double a = from16(o1[i], false), b = from16(o2[i], false);
+      mo = std::max(mo, fabs(a - b));
+      sym = std::max(sym, fabs(a - b) / (fabs(a) + fabs(b) + 1e-5));
+    }
+    for (size_t i = 0; i < ns; ++i) {
+      const double la = hm1[i] + log((double)hl1[i]), lb = hm2[i] + log((double)hl2[i]);
+      mlse = std::max(mlse, fabs(la - lb) / std::max(1.0, fabs(la)));
+      mm = std::max(mm, fabs((double)hm1[i] - hm2[i]));
+    }
+    const bool pass = mo <= 2e-3 && mlse <= 1e-4 && sym < 0.02;
+    printf("RESULT ref %s vs reference flash_attention_forward  B=%d H=%d N=%d d=%d M=%d set=%c  O_maxabs=%.3e lse_rel=%.3e m_abs=%.3e sym_rel=%.5f\n",
+           pass ? "PASS" : "FAIL", B, H, N, d, M, set, mo, mlse, mm, sym);
+    if (iters > 0 && set == 'S') {
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      ref(dQ, dK, dV, dO1, l1, m1, B, H, N, d, M, nullptr);
+      cudaEventRecord(e0);
+      for (int i = 0; i < iters; ++i) ref(dQ, dK, dV, dO1, l1, m1, B, H, N, d, M, nullptr);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+      printf("TIMING ref flash_attention_forward(sm_100a build) B=%d H=%d N=%d d=%d M=%d: %.3f ms -> %.3f TFLOP/s\n", B, H, N, d, M,
+             ms, 4.0 * BH * (double)N * N * d / ms * 1e-9);
+    }
+    cudaFree(dQ); cudaFree(dK); cudaFree(dV); cudaFree(dO1); cudaFree(dO2); cudaFree(l1); cudaFree(m1); cudaFree(l2); cudaFree(m2);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ umma
+struct UnitArgs {
+  unsigned long long desc_hi_qk, desc_hi_v;
+  unsigned int idesc_qk, idesc_pv;
+  unsigned int kstep_v_bytes;
+};
+
+template <int D>
+__global__ void __launch_bounds__(128, 1)
+umma_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmV, const float* __restrict__ Pin, float* __restrict__ Sout,
+                 float* __restrict__ Oout, const UnitArgs a) {
+  using namespace fa;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t kTile = 128 * D * 2, kBox = 128 * 64 * 2;
+  const uint32_t sA = base, sB = base + kTile, sV = base + 2 * kTile, bars = base + 3 * kTile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bars, 1); mbar_init(bars + 8, 1); mbar_init(bars + 16, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc<512>(bars + 32); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(bars + 32));
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bars, 3 * kTile);
+    for (int h = 0; h < D / 64; ++h) {
+      tma_load_3d(sA + h * kBox, &tmA, bars, h * 64, 0, 0);
+      tma_load_3d(sB + h * kBox, &tmB, bars, h * 64, 0, 0);
+      tma_load_3d(sV + h * kBox, &tmV, bars, h * 64, 0, 0);
+    }
+    mbar_wait(bars, 0, 1);
+    tc_fence_after();
+    for (int k = 0; k < D / 16; ++k) {
+      const uint32_t off = (k / 4) * kBox + (k % 4) * 32;
+      umma_ss(tmem, umma_desc(a.desc_hi_qk, sA + off), umma_desc(a.desc_hi_qk, sB + off), a.idesc_qk, k > 0);
+    }
+    umma_commit(bars + 8);
+  }
+  __syncwarp();
+  mbar_wait(bars + 8, 0, 2);
+  tc_fence_after();
+  const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+  const int row = warp * 32 + lane;
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[32];
+    tmem_ld32(tmem + lane_addr + q * 32, r);
+    tmem_wait_ld();
+    for (int k = 0; k < 32; ++k) Sout[row * 128 + q * 32 + k] = __uint_as_float(r[k]);
+  }
+  // P (bf16) -> TMEM columns [256, 320)
+  for (int q = 0; q < 4; ++q) {
+    uint32_t pk[16];
+    for (int k = 0; k < 16; ++k) {
+      __nv_bfloat162 v = __floats2bfloat162_rn(Pin[row * 128 + q * 32 + 2 * k], Pin[row * 128 + q * 32 + 2 * k + 1]);
+      pk[k] = *reinterpret_cast<uint32_t*>(&v);
+    }
+    tmem_st16(tmem + lane_addr + 256 + q * 16, pk);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 8; ++k)
+      umma_ts(tmem + 128, tmem + 256 + k * 8, umma_desc(a.desc_hi_v, sV + k * a.kstep_v_bytes), a.idesc_pv, k > 0);
+    umma_commit(bars + 16);
+  }
+  __syncwarp();
+  mbar_wait(bars + 16, 0, 3);
+  tc_fence_after();
+  for (int q = 0; q < D / 32; ++q) {
+    uint32_t r[32];
+    tmem_ld32(tmem + lane_addr + 128 + q * 32, r);
+    tmem_wait_ld();
+    for (int k = 0; k < 32; ++k) Oout[row * D + q * 32 + k] = __uint_as_float(r[k]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tmem); }
+}
+
+static int make_tmap_2d(CUtensorMap* tm, void* base, int d, int rows) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  using Enc = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)rows * d * 2};
+  cuuint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+  CUresult r = ((Enc)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+template <int D>
+static int run_umma_d(int argc, char** argv) {
+  UnitArgs a;
+  const unsigned lbo_v = argc > 3 ? atoi(argv[3]) : 16384, sbo_v = argc > 4 ? atoi(argv[4]) : 1024;
+  a.kstep_v_bytes = argc > 5 ? atoi(argv[5]) : 2048;
+  const unsigned lbo_qk = argc > 6 ? atoi(argv[6]) : 16, sbo_qk = argc > 7 ? atoi(argv[7]) : 1024;
+  a.desc_hi_qk = fa::umma_desc_hi_bits(lbo_qk, sbo_qk, 2);
+  a.desc_hi_v = fa::umma_desc_hi_bits(lbo_v, sbo_v, 2);
+  a.idesc_qk = fa::umma_idesc(1, 0, 0, 128, 128);
+  a.idesc_pv = fa::umma_idesc(1, 0, 1, 128, D);
+  const size_t n = 128 * D;
+  std::vector<float> A(n), Bm(n), V(n), P(128 * 128);
+  fixture_normal_bf16(A.data(), n, 11, 1.f);
+  fixture_normal_bf16(Bm.data(), n, 12, 1.f);
+  fixture_normal_bf16(V.data(), n, 13, 1.f);
+  fixture_uniform_bf16(P.data(), 128 * 128, 14, 0.f, 1.f);
+  auto a16 = to16(A, true), b16 = to16(Bm, true), v16 = to16(V, true);
+  void *dA, *dB, *dV; float *dP, *dS, *dO;
+  CK(cudaMalloc(&dA, n * 2)); CK(cudaMalloc(&dB, n * 2)); CK(cudaMalloc(&dV, n * 2));
+  CK(cudaMalloc(&dP, 128 * 128 * 4)); CK(cudaMalloc(&dS, 128 * 128 * 4)); CK(cudaMalloc(&dO, n * 4));
+  CK(cudaMemcpy(dA, a16.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, b16.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dV, v16.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dP, P.data(), 128 * 128 * 4, cudaMemcpyHostToDevice));
+  CUtensorMap tA, tB, tV;
+  if (make_tmap_2d(&tA, dA, D, 128) || make_tmap_2d(&tB, dB, D, 128) || make_tmap_2d(&tV, dV, D, 128)) {
+    printf("RESULT umma FAIL tensor map encode\n");
+    return 1;
+  }
+  const int smem = 1024 + 3 * 128 * D * 2 + 64;
+  CK(cudaFuncSetAttribute(umma_unit_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_unit_kernel<D><<<1, 128, smem>>>(tA, tB, tV, dP, dS, dO, a);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("RESULT umma FAIL kernel error %s\n", cudaGetErrorString(e)); return 1; }
+  std::vector<float> S(128 * 128), O(n);
+  CK(cudaMemcpy(S.data(), dS, 128 * 128 * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(O.data(), dO, n * 4, cudaMemcpyDeviceToHost));
+  double es = 0, eo = 0, ms = 0, mo = 0;
+  for (int i = 0; i < 128; ++i)
+    for (int j = 0; j < 128; ++j) {
+      double acc = 0;
+      for (int t = 0; t < D; ++t) acc += (double)A[i * D + t] * Bm[j * D + t];
+      es = std::max(es, fabs(acc - S[i * 128 + j])); ms = std::max(ms, fabs(acc));
+    }
+  for (int i = 0; i < 128; ++i)
+    for (int c = 0; c < D; ++c) {
+      double acc = 0;
+      for (int kk = 0; kk < 128; ++kk) acc += (double)from16(to16({P[i * 128 + kk]}, true)[0], true) * V[kk * D + c];
+      eo = std::max(eo, fabs(acc - O[i * D + c])); mo = std::max(mo, fabs(acc));
+    }
+  const bool ps = es < 1e-3 * ms, po = eo < 1e-3 * mo;
+  printf("RESULT umma D=%d lbo_v=%u sbo_v=%u kstep_v=%u lbo_qk=%u sbo_qk=%u : QK^T %s (err %.3e / max %.2f)  P.V %s (err %.3e / max %.2f)\n",
+         D, lbo_v, sbo_v, a.kstep_v_bytes, lbo_qk, sbo_qk, ps ? "PASS" : "FAIL", es, ms, po ? "PASS" : "FAIL", eo, mo);
+  if (!ps) printf("  S[0][0..3] = %.3f %.3f %.3f %.3f ; S[1][0]=%.3f S[8][0]=%.3f S[0][64]=%.3f\n", S[0], S[1], S[2], S[3], S[128], S[8 * 128], S[64]);
+  if (!po) printf("  O[0][0..3] = %.3f %.3f %.3f %.3f ; O[1][0]=%.3f O[0][%d]=%.3f\n", O[0], O[1], O[2], O[3], O[D], D - 1, O[D - 1]);
+  return (ps && po) ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: fa_selftest attn|umma|ref ...\n"); return 2; }
+  std::string mode = argv[1];
+  if (mode == "attn") return run_attn(argc, argv);
+  if (mode == "ref") return run_ref(argc, argv);
+  if (mode == "umma") {
+    const int D = argc > 2 ? atoi(argv[2]) : 128;
+    return D == 64 ? run_umma_d<64>(argc, argv) : run_umma_d<128>(argc, argv);
+  }
+  return 2;
+}
