@@ -1,0 +1,31 @@
+"""flash_attention_impls_b200 — B200 (sm_100a) FlashAttention forward behind the reference's launch surface.
+
+The product is `lib/libfa_b200.so` (C ABI: include/fa_b200.h).  This package is the thin host-side
+mirror of the reference's operator interface plus the multi-GPU drivers ((b,h) sharding, ring attention).
+"""
+from ._lib import FaB200Error, LIB_PATH, launch_count, load  # noqa: F401
+from .ops import (  # noqa: F401
+    attention_forward,
+    attention_reference_dispatch,
+    cast_output,
+    flash_attention,
+    flash_attention_cutlass_dispatch,
+    flash_attention_forward,
+    flash_attention_forward_dispatch,
+    flash_attention_small_tile_dispatch,
+    flash_attention_with_stats,
+    merge_partial,
+)
+from .parallel import (  # noqa: F401
+    bh_shard_range,
+    ring_attention,
+    zigzag_gather,
+    zigzag_split,
+)
+
+__all__ = [
+    "attention_forward", "flash_attention", "flash_attention_with_stats", "flash_attention_forward",
+    "flash_attention_cutlass_dispatch", "flash_attention_forward_dispatch",
+    "flash_attention_small_tile_dispatch", "attention_reference_dispatch", "merge_partial", "cast_output",
+    "ring_attention", "zigzag_split", "zigzag_gather", "bh_shard_range", "launch_count", "load",
+]

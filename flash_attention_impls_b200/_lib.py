@@ -1,0 +1,94 @@
+"""ctypes binding of libfa_b200.so (the C ABI declared in include/fa_b200.h).
+
+There is no CPU or PyTorch fallback: if the CUDA library is missing, importing the symbols raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfa_b200.so")
+
+FA_B200_FP16 = 0
+FA_B200_BF16 = 1
+
+STATUS = {
+    0: "FA_B200_OK", 1: "FA_B200_ERR_NULL", 2: "FA_B200_ERR_SHAPE", 3: "FA_B200_ERR_HEAD_DIM",
+    4: "FA_B200_ERR_DTYPE", 5: "FA_B200_ERR_ALIGNMENT", 6: "FA_B200_ERR_ARCH", 7: "FA_B200_ERR_CUDA",
+    8: "FA_B200_ERR_DRIVER",
+}
+
+# every symbol include/fa_b200.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "fa_b200_forward", "fa_b200_forward_legacy", "fa_b200_forward_fp16", "fa_b200_merge_partial",
+    "fa_b200_cast_output", "fa_b200_launch_count", "fa_b200_last_error", "fa_b200_status_string",
+    "fa_b200_version",
+)
+
+
+class FaB200Params(Structure):
+    """Mirror of `struct fa_b200_params` (include/fa_b200.h)."""
+    _fields_ = [
+        ("Q", c_void_p), ("K", c_void_p), ("V", c_void_p), ("O", c_void_p),
+        ("lse", c_void_p), ("l", c_void_p), ("m", c_void_p),
+        ("B", c_int), ("H", c_int), ("N", c_int), ("d", c_int),
+        ("N_kv", c_int), ("dtype", c_int), ("causal", c_int), ("softmax_scale", c_float),
+        ("q_stride_bh", c_int64), ("kv_stride_bh", c_int64), ("o_stride_bh", c_int64),
+        ("stat_stride_bh", c_int64),
+        ("stream", c_void_p),
+    ]
+
+
+class FaB200Error(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libfa_b200.so; raises (loudly) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make lib` (or `python -c 'import __graft_entry__ as g; "
+            "g.build()'`). flash_attention_impls_b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.fa_b200_forward.argtypes = [POINTER(FaB200Params)]
+    lib.fa_b200_forward.restype = c_int
+    lib.fa_b200_forward_legacy.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.fa_b200_forward_legacy.restype = c_int
+    lib.fa_b200_forward_fp16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_void_p]
+    lib.fa_b200_forward_fp16.restype = c_int
+    lib.fa_b200_merge_partial.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]
+    lib.fa_b200_merge_partial.restype = c_int
+    lib.fa_b200_cast_output.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]
+    lib.fa_b200_cast_output.restype = c_int
+    lib.fa_b200_launch_count.argtypes = []
+    lib.fa_b200_launch_count.restype = c_uint64
+    lib.fa_b200_last_error.argtypes = []
+    lib.fa_b200_last_error.restype = c_char_p
+    lib.fa_b200_status_string.argtypes = [c_int]
+    lib.fa_b200_status_string.restype = c_char_p
+    lib.fa_b200_version.argtypes = []
+    lib.fa_b200_version.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise FaB200Error(status, load().fa_b200_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(load().fa_b200_launch_count())
