@@ -1,0 +1,105 @@
+"""CPU tests of the drop-in boundary: libfa_b200.so loads, exports every symbol include/fa_b200.h
+declares, and validates its arguments without touching a GPU (no compute calls here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from flash_attention_impls_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fa_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fa_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_functions() == sorted(_lib.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in _declared_functions():
+        assert getattr(lib, name) is not None
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    for name in _declared_functions():
+        assert re.search(rf"\bT {name}\b", out), f"{name} is not an exported text symbol"
+
+
+def test_reference_named_cxx_shims_are_exported():
+    """flash_attention_cutlass_dispatch & co keep the reference's C++ linkage (flash_attn_cutlass.cu:519-529)."""
+    out = subprocess.check_output(["nm", "-D", "-C", "--defined-only", _lib.LIB_PATH], text=True)
+    for fn in ("flash_attention_cutlass_dispatch", "flash_attention_forward_dispatch",
+               "flash_attention_small_tile_dispatch", "attention_reference_dispatch"):
+        assert re.search(rf"{fn}\(cutlass::half_t const\*, cutlass::half_t const\*, cutlass::half_t const\*, "
+                         rf"cutlass::half_t\*, int, int, int, int, CUstream_st\*\)", out), fn
+
+
+def test_struct_layout_matches_header():
+    # 7 pointers, 7 ints + float, 4 int64, 1 pointer  (x86-64 LP64)
+    assert ctypes.sizeof(_lib.FaB200Params) == 7 * 8 + 8 * 4 + 4 * 8 + 8
+
+
+def test_version_and_status_strings():
+    lib = _lib.load()
+    assert lib.fa_b200_version() == (0 << 16) | 1
+    assert lib.fa_b200_status_string(0) == b"ok"
+    assert lib.fa_b200_status_string(3) == b"unsupported head_dim"
+    assert lib.fa_b200_status_string(99) == b"unknown status"
+
+
+def _params(**kw):
+    p = _lib.FaB200Params()
+    p.Q = p.K = p.V = p.O = 0x1000          # never dereferenced: validation fails first
+    p.B, p.H, p.N, p.d = 1, 1, 128, 64
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+@pytest.mark.parametrize("kw,status", [
+    (dict(Q=None), 1), (dict(O=None), 1), (dict(B=0), 2), (dict(N=-5), 2), (dict(N_kv=-1), 2),
+    (dict(d=32), 3), (dict(d=96), 3), (dict(d=256), 3), (dict(dtype=7), 4),
+    (dict(Q=0x1008), 5), (dict(q_stride_bh=8 * 1024 + 4), 5), (dict(q_stride_bh=64), 2),
+])
+def test_argument_validation_returns_codes_without_a_gpu(kw, status):
+    """Error convention of SURVEY.md section 8b: an int status instead of the reference's stderr +
+    silent no-launch on unsupported head_dim (flash_attn_cutlass.cu:540-542)."""
+    lib = _lib.load()
+    rc = lib.fa_b200_forward(ctypes.byref(_params(**kw)))
+    assert rc == status
+    assert lib.fa_b200_last_error() != b""
+    assert lib.fa_b200_forward(None) == 1
+
+
+def test_merge_and_cast_validation():
+    lib = _lib.load()
+    assert lib.fa_b200_merge_partial(None, None, None, None, 4, 64, 1, None) == 1
+    assert lib.fa_b200_merge_partial(0x1000, 0x1000, 0x1000, 0x1000, 4, 60, 1, None) == 2
+    assert lib.fa_b200_cast_output(0x1000, 0x1000, 4, 64, 5, None) == 4
+
+
+def test_no_cpu_fallback_in_python_surface():
+    import torch
+    import flash_attention_impls_b200 as fa
+    q = torch.zeros(1, 1, 128, 64, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fa.flash_attention(q, q, q)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fa.attention_forward(q, q, q)
+
+
+def test_product_package_does_not_import_oracle():
+    """The oracle is the checker only: nothing under flash_attention_impls_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "flash_attention_impls_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle." not in text and "import oracle" not in text and "liboracle" not in text, f

@@ -1,0 +1,307 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ctypes) against the CPU oracle on the same
+seeded inputs, against the committed golden vectors of the reference's sdpa_reference, against the
+reference's own CUDA FA1 kernel (oracle/_ref, when it was built), and — at BASELINE's full sizes —
+through size-independent properties.
+
+Tolerances (BASELINE.json north_star): O max-abs-error <= 2e-3 (bf16/fp16 in, fp32 accumulate),
+logsumexp within 1e-4 relative (|d| <= 1e-4 * max(1, |lse|)).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+O_TOL = 2e-3
+LSE_TOL = 1e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fa():
+    assert torch.cuda.is_available()
+    import flash_attention_impls_b200 as fa
+    fa.load()
+    return fa
+
+
+def _dt(name):
+    return torch.bfloat16 if name == "bf16" else torch.float16
+
+
+def _run(fa, q, k, v, dtype, causal, stats=True):
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, dtype) for x in (q, k, v))
+    B, H, N, _ = q.shape
+    l = torch.empty((B, H, N), dtype=torch.float32, device=dev) if stats else None
+    m = torch.empty_like(l) if stats else None
+    before = fa.launch_count()
+    o, lse = fa.attention_forward(tq, tk, tv, causal=causal, l=l, m=m)
+    torch.cuda.synchronize()
+    assert fa.launch_count() == before + 1           # the CUDA kernel really launched
+    return o.float().cpu().numpy(), lse.cpu().numpy(), (l.cpu().numpy() if stats else None), (m.cpu().numpy() if stats else None)
+
+
+def _check(o, lse, o_ref, lse_ref):
+    assert np.isfinite(o).all()
+    assert np.abs(o - o_ref).max() <= O_TOL
+    fin = np.isfinite(lse_ref)
+    assert np.array_equal(np.isfinite(lse), fin)
+    if fin.any():
+        assert (np.abs(lse[fin] - lse_ref[fin]) / np.maximum(1.0, np.abs(lse_ref[fin]))).max() <= LSE_TOL
+
+
+SHAPES = [
+    # B, H, N, Nkv, d, dtype, causal
+    (1, 1, 128, 128, 64, "fp16", False),      # c1's shape on the GPU path
+    (1, 1, 128, 128, 128, "bf16", False),
+    (1, 1, 1, 1, 64, "fp16", False),          # smallest possible
+    (1, 1, 1, 1, 128, "bf16", True),
+    (1, 3, 127, 127, 64, "bf16", True),       # ragged, one short of a tile
+    (1, 2, 129, 129, 128, "fp16", True),      # ragged, one over a tile
+    (2, 2, 257, 257, 128, "bf16", False),     # one over a CTA (256 rows)
+    (1, 2, 1000, 1000, 128, "bf16", True),
+    (2, 3, 777, 777, 64, "fp16", False),
+    (1, 2, 1024, 1024, 64, "bf16", True),
+    (1, 2, 2048, 2048, 128, "bf16", False),
+    (1, 1, 300, 900, 128, "bf16", False),     # cross lengths N_kv > N
+    (1, 2, 300, 900, 64, "bf16", True),       # causal, bottom-right aligned
+    (1, 2, 900, 300, 128, "fp16", True),      # N_kv < N: the first 600 rows see no key -> O = 0, lse = -inf
+    (1, 1, 512, 130, 128, "bf16", False),
+]
+
+
+@pytest.mark.parametrize("B,H,N,Nkv,d,dtype,causal", SHAPES)
+def test_attention_matches_oracle(fa, B, H, N, Nkv, d, dtype, causal):
+    from oracle import oracle
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, Nkv, d))
+    o, lse, l, m = _run(fa, q, k, v, _dt(dtype), causal)
+    o_ref, lse_ref, l_ref, m_ref = oracle.attention(q, k, v, causal=causal)
+    _check(o, lse, o_ref, lse_ref)
+    fin = np.isfinite(lse_ref)
+    # the reference's per-row outputs (flashAttention.cu:115-120,137-138): m = true row max, l = sum exp(s - m)
+    assert np.abs(m[fin] - m_ref[fin]).max() <= 1e-4
+    assert (np.abs(l[fin] - l_ref[fin]) / np.maximum(1.0, l_ref[fin])).max() <= 1e-4
+    assert np.all(o[~fin] == 0)
+
+
+@pytest.mark.parametrize("name", ["c1_fp32_noncausal", "causal_d64", "causal_ragged_d128", "noncausal_ragged_d128", "setR_d64"])
+def test_attention_matches_reference_sdpa_golden(fa, golden, name):
+    """Committed outputs of the reference's own Python oracle (FA2-triton.py:311-323)."""
+    q, k, v = (golden[f"{name}/{t}"].astype(np.float32) for t in "qkv")
+    causal = bool(golden[f"{name}/causal"])
+    for dtype in (torch.float16, torch.bfloat16):
+        if dtype == torch.bfloat16 and name == "setR_d64":
+            continue                             # Set R is only fp16-exact
+        o, lse, _, _ = _run(fa, q, k, v, dtype, causal, stats=False)
+        assert np.abs(o - golden[f"{name}/o"]).max() <= O_TOL
+
+
+def test_reference_input_distribution_set_r(fa):
+    """The reference's own test inputs: mt19937(42), N(0,0.02), Q == K == V (main.cu:43-61), with its own
+    gate: symmetric relative error < 2 % (main.cu:346) evaluated where it is meaningful (|ref| > 1e-3)."""
+    from oracle import oracle
+    B, H, N, d = 1, 4, 512, 64
+    q, k, v = oracle.set_r((B, H, N, d))
+    q = q.astype(np.float16).astype(np.float32); k = q.copy(); v = q.copy()
+    o, lse, _, _ = _run(fa, q, k, v, torch.float16, False)
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v)
+    _check(o, lse, o_ref, lse_ref)
+    big = np.abs(o_ref) > 1e-3
+    assert (np.abs(o - o_ref)[big] / (np.abs(o)[big] + np.abs(o_ref)[big] + 1e-5)).max() < 0.02
+
+
+def test_large_score_range_exercises_lazy_rescale(fa):
+    """Row maxima that keep growing along the key axis force the lazy O/l rescale path many times."""
+    from oracle import oracle
+    B, H, N, d = 1, 2, 1024, 128
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d), seeds=(31, 32, 33))
+    ramp = (1.0 + 6.0 * np.arange(N, dtype=np.float32) / N)[None, None, :, None]
+    k = (k * ramp).astype(np.float32)
+    k = torch.from_numpy(k).to(torch.bfloat16).float().numpy()        # keep inputs bf16-exact
+    o, lse, l, m = _run(fa, q, k, v, torch.bfloat16, False)
+    o_ref, lse_ref, l_ref, m_ref = oracle.attention(q, k, v)
+    _check(o, lse, o_ref, lse_ref)
+    assert np.abs(m - m_ref).max() <= 1e-3 and (np.abs(l - l_ref) / l_ref).max() <= 1e-3
+
+
+def test_softmax_scale_argument(fa):
+    from oracle import oracle
+    q, k, v = oracle.set_s((1, 2, 256, 64), (1, 2, 256, 64))
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, torch.bfloat16) for x in (q, k, v))
+    o, lse = fa.attention_forward(tq, tk, tv, softmax_scale=0.05)
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v, scale=0.05)
+    _check(o.float().cpu().numpy(), lse.cpu().numpy(), o_ref, lse_ref)
+
+
+def test_reference_surface_entry_points(fa):
+    """flash_attention (FA2-triton.py:240-244), flash_attention_forward argument list (flashAttention.h:8-11)
+    and flash_attention_cutlass_dispatch (flash_attn_cutlass.cu:519-529) all give the same result."""
+    from oracle import oracle
+    B, H, N, d = 2, 2, 384, 64
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d))
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, torch.float16) for x in (q, k, v))
+    o_ref, lse_ref, l_ref, m_ref = oracle.attention(q, k, v)
+    o1 = fa.flash_attention(tq, tk, tv, causal=False)
+    O2 = torch.empty_like(tq); l = torch.empty((B, H, N), dtype=torch.float32, device=dev); m = torch.empty_like(l)
+    fa.flash_attention_forward(tq, tk, tv, O2, l, m, B, H, N, d, 16384)
+    O3 = torch.empty_like(tq)
+    fa.flash_attention_cutlass_dispatch(tq, tk, tv, O3, B, H, N, d)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, O2) and torch.equal(o1, O3)
+    assert np.abs(o1.float().cpu().numpy() - o_ref).max() <= O_TOL
+    assert np.abs((m + torch.log(l)).cpu().numpy() - lse_ref).max() <= 1e-4
+    # fp32 inputs are down-cast to fp16 and the result cast back, as in the reference (FA2-triton.py:242-244)
+    o4 = fa.flash_attention(tq.float(), tk.float(), tv.float(), causal=True)
+    assert o4.dtype == torch.float32
+    o5, m5, l5 = fa.flash_attention_with_stats(tq, tk, tv, causal=True)
+    oc, lsec, _, _ = oracle.attention(q, k, v, causal=True)
+    assert np.abs(o4.cpu().numpy() - oc).max() <= O_TOL and np.abs(o5.float().cpu().numpy() - oc).max() <= O_TOL
+    assert np.abs((m5 + torch.log(l5)).cpu().numpy() - lsec).max() <= 1e-4
+
+
+def test_unsupported_head_dim_is_an_error_not_a_silent_skip(fa):
+    dev = torch.device("cuda:0")
+    x = torch.zeros(1, 1, 128, 32, dtype=torch.float16, device=dev)
+    with pytest.raises(fa.FaB200Error) as e:
+        fa.attention_forward(x, x, x)
+    assert e.value.status == 3
+
+
+def test_strided_bh_views(fa):
+    """Row sub-ranges of a longer sequence (what the ring driver passes): (b,h) stride != N*d."""
+    from oracle import oracle
+    B, H, N, d = 1, 3, 512, 128
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d))
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, torch.bfloat16) for x in (q, k, v))
+    out = torch.zeros_like(tq); lse = torch.full((B, H, N), float("-inf"), dtype=torch.float32, device=dev)
+    fa.attention_forward(tq[:, :, 256:], tk[:, :, :384], tv[:, :, :384], out=out[:, :, 256:], lse=lse[:, :, 256:])
+    torch.cuda.synchronize()
+    o_ref, lse_ref, _, _ = oracle.attention(q[:, :, 256:], k[:, :, :384], v[:, :, :384])
+    _check(out[:, :, 256:].float().cpu().numpy(), lse[:, :, 256:].cpu().numpy(), o_ref, lse_ref)
+    assert torch.all(out[:, :, :256] == 0) and torch.all(torch.isinf(lse[:, :, :256]))   # untouched rows
+
+
+def test_merge_partial_kernel(fa):
+    """attention over [K1;K2] == merge(attention(K1), attention(K2)) (the ring-attention identity)."""
+    from oracle import oracle
+    B, H, N, d = 1, 2, 512, 128
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, 1024, d))
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, torch.bfloat16) for x in (q, k, v))
+    o_acc = torch.zeros((B, H, N, d), dtype=torch.float32, device=dev)
+    lse_acc = torch.full((B, H, N), float("-inf"), dtype=torch.float32, device=dev)
+    for lo, hi in ((0, 384), (384, 1024)):
+        op, lp = fa.attention_forward(tq, tk[:, :, lo:hi].contiguous(), tv[:, :, lo:hi].contiguous())
+        fa.merge_partial(o_acc, lse_acc, op, lp)
+    out = fa.cast_output(o_acc, torch.bfloat16)
+    torch.cuda.synchronize()
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v)
+    _check(out.float().cpu().numpy(), lse_acc.cpu().numpy(), o_ref, lse_ref)
+
+
+@pytest.mark.parametrize("N,d,M", [(512, 64, 4096), (1024, 128, 16384)])
+def test_against_reference_cuda_fa1_kernel(fa, N, d, M):
+    """The reference's own kernel flash_attention_forward (flashAttention.cu:7-152), compiled unmodified for
+    sm_100a into oracle/_ref/libref_fa1.so, on the same fp16 inputs."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_fa1.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_fa1.so not built (needs /root/reference at build time)")
+    from oracle import oracle
+    ref = ctypes.CDLL(path)
+    ref.ref_fa1_forward.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    B, H = 1, 2
+    dev = torch.device("cuda:0")
+    for maker in (lambda: oracle.set_s((B, H, N, d), (B, H, N, d)), lambda: oracle.set_r((B, H, N, d))):
+        q, k, v = maker()
+        tq, tk, tv = (torch.from_numpy(x).to(dev, torch.float16) for x in (q, k, v))
+        O1 = torch.empty_like(tq); l1 = torch.empty((B, H, N), dtype=torch.float32, device=dev); m1 = torch.empty_like(l1)
+        O2 = torch.empty_like(tq); l2 = torch.empty_like(l1); m2 = torch.empty_like(l1)
+        torch.cuda.synchronize()
+        assert ref.ref_fa1_forward(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), O1.data_ptr(), l1.data_ptr(),
+                                   m1.data_ptr(), B, H, N, d, M, None) == 0
+        fa.flash_attention_forward(tq, tk, tv, O2, l2, m2, B, H, N, d, M)
+        torch.cuda.synchronize()
+        assert (O1.float() - O2.float()).abs().max().item() <= O_TOL
+        lse1, lse2 = m1 + torch.log(l1), m2 + torch.log(l2)
+        assert ((lse1 - lse2).abs() / lse1.abs().clamp(min=1.0)).max().item() <= LSE_TOL
+        assert (m1 - m2).abs().max().item() <= 1e-4
+
+
+# ------------------------------------------------------------------ full BASELINE sizes: properties
+def _full_inputs(B, H, N, d, dtype, seed=7):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    q = torch.randn((B, H, N, d), generator=g, device=dev).to(dtype)
+    k = torch.randn((B, H, N, d), generator=g, device=dev).to(dtype)
+    v = (torch.rand((B, H, N, d), generator=g, device=dev) - 0.5).to(dtype)
+    return q, k, v
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_full_size_c3_c4_properties(fa, causal):
+    """B=4 H=32 N=8192 d=128 bf16 (BASELINE c3 / c4): sampled rows vs the oracle, (b,h)-shard equivalence
+    (bit-exact), split-key merge identity, and the causal first-row identity O[0] = V[0]."""
+    from oracle import oracle
+    B, H, N, d = 4, 32, 8192, 128
+    q, k, v = _full_inputs(B, H, N, d, torch.bfloat16)
+    o, lse = fa.attention_forward(q, k, v, causal=causal)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    # (1) oracle on sampled rows of sampled heads
+    for (b, h) in ((0, 0), (3, 31), (1, 17)):
+        qn, kn, vn = (t[b:b + 1, h:h + 1].float().cpu().numpy() for t in (q, k, v))
+        for r0 in (0, 4032, 8128):
+            o_ref, lse_ref, _, _ = oracle.attention(qn, kn, vn, causal=causal, row_begin=r0, row_end=r0 + 64)
+            got = o[b, h, r0:r0 + 64].float().cpu().numpy()
+            assert np.abs(got - o_ref[0, 0, r0:r0 + 64]).max() <= O_TOL
+            gl = lse[b, h, r0:r0 + 64].cpu().numpy()
+            assert (np.abs(gl - lse_ref[0, 0, r0:r0 + 64]) / np.maximum(1, np.abs(lse_ref[0, 0, r0:r0 + 64]))).max() <= LSE_TOL
+    # (2) (b,h) sharding: each shard computed alone is bit-identical to the full launch
+    for P, r in ((8, 3), (2, 1)):
+        b0, b1 = fa.bh_shard_range(B * H, P, r)
+        qs, ks, vs = (t.view(1, B * H, N, d)[:, b0:b1] for t in (q, k, v))
+        os_, ls_ = fa.attention_forward(qs, ks, vs, causal=causal)
+        assert torch.equal(os_, o.view(1, B * H, N, d)[:, b0:b1]) and torch.equal(ls_, lse.view(1, B * H, N)[:, b0:b1])
+    # (3) causal: the first query row sees only key 0 -> O[0] == V[0] exactly, lse == s_00
+    if causal:
+        assert torch.equal(o[:, :, 0], v[:, :, 0])
+    else:
+        # (4) non-causal: split the keys in two, merge the partials with their lse -> same result
+        qh, kh, vh = q[:1, :4], k[:1, :4], v[:1, :4]
+        o_acc = torch.zeros(qh.shape, dtype=torch.float32, device=q.device)
+        l_acc = torch.full(qh.shape[:3], float("-inf"), dtype=torch.float32, device=q.device)
+        for lo, hi in ((0, 5000), (5000, N)):
+            op, lp = fa.attention_forward(qh, kh[:, :, lo:hi].contiguous(), vh[:, :, lo:hi].contiguous())
+            fa.merge_partial(o_acc, l_acc, op, lp)
+        assert (o_acc - o[:1, :4].float()).abs().max().item() <= O_TOL
+        assert (l_acc - lse[:1, :4]).abs().max().item() <= 1e-3
+
+
+def test_full_size_c2(fa):
+    """B=8 H=16 N=1024 d=64 fp16 non-causal (the reference's cuda_fa1 benchmark shape, BASELINE c2): full oracle check."""
+    from oracle import oracle
+    B, H, N, d = 8, 16, 1024, 64
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d))
+    o, lse, l, m = _run(fa, q, k, v, torch.float16, False)
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v)
+    _check(o, lse, o_ref, lse_ref)
+
+
+def test_host_pipeline_e2e_matches_device_path(fa):
+    B, H, N, d = 2, 8, 1024, 128
+    q, k, v = _full_inputs(B, H, N, d, torch.bfloat16, seed=9)
+    o, lse = fa.attention_forward(q, k, v, causal=True)
+    pipe = fa.HostPipeline(B, H, N, d, torch.bfloat16, causal=True, chunks=5)
+    hq, hk, hv = (t.cpu().pin_memory() for t in (q, k, v))
+    ho = torch.empty_like(hq).pin_memory(); hl = torch.empty((B, H, N), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        pipe(hq, hk, hv, ho, hl)
+    pipe.synchronize()
+    assert torch.equal(ho, o.cpu()) and torch.equal(hl, lse.cpu())
