@@ -22,7 +22,7 @@ tools/fa_selftest: tools/fa_selftest.cu $(PKG)/lib/libfa_b200.so oracle
 	  -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)/lib' -Xlinker -rpath -Xlinker '$$ORIGIN/../oracle'
 
 sass: $(PKG)/lib/libfa_b200.so
-	cuobjdump -sass $< > profiles/libfa_b200.sass
+	cuobjdump -sass $< > /tmp/libfa_b200.sass
 
 clean:
 	rm -f $(PKG)/lib/*.so tools/fa_selftest; $(MAKE) -C oracle clean

@@ -101,23 +101,35 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_attention_sample(B, H, N, d, causal, target_s, threads):
     """Times the oracle port (naive fp32 softmax(QK^T)V restating main.cu:165-202) on the host cores on a
-    bounded sample of the workload: `rows` query rows of one (b,h) slice against all N keys."""
-    import numpy as np
+    bounded sample of the workload: the last `rows` query rows of `nbh` (b,h) slices against all N keys,
+    sized from a short calibration run to take about `target_s` seconds."""
     from oracle import oracle
-    q, k, v = oracle.set_s((1, 1, N, d), (1, 1, N, d))
-    def run(rows):
+    max_bh = min(B * H, 8)
+    q, k, v = oracle.set_s((1, max_bh, N, d), (1, max_bh, N, d))
+
+    def run(sample):
+        nbh, rows = sample
         r0 = N - rows            # the last rows: for causal runs these see (almost) all keys
         t0 = time.perf_counter()
-        oracle.attention(q, k, v, causal=causal, nthreads=threads, row_begin=r0, row_end=N)
+        oracle.attention(q[:, :nbh], k[:, :nbh], v[:, :nbh], causal=causal, nthreads=threads, row_begin=r0, row_end=N)
         dt = time.perf_counter() - t0
-        fl = 4.0 * rows * N * d
+        fl = 4.0 * rows * N * d * nbh
         if causal:               # rows r0..N-1 see r+1 keys each
-            fl = 4.0 * d * (rows * (r0 + N + 1) / 2.0)
+            fl = 4.0 * d * (rows * (r0 + N + 1) / 2.0) * nbh
         return dt, fl
-    rows = min(N, 64)
-    dt, fl = run(rows)
-    rows = int(max(16, min(N, rows * target_s / max(dt, 1e-4))))
-    return rows, run
+    cal_rows = min(N, 128)
+    dt, fl = run((1, cal_rows))
+    want_rows = cal_rows * target_s / max(dt, 1e-4)
+    if want_rows <= N:
+        sample = (1, int(max(16, want_rows)))
+    else:
+        sample = (int(min(max_bh, max(1, round(want_rows / N)))), N)
+    return sample, run
+
+
+def sample_text(sample, N, d, causal):
+    return (f"last {sample[1]} query rows x {N} keys of {sample[0]} (b,h) slice(s), d={d}, fp32 naive "
+            f"softmax(QK^T)V (oracle port of main.cu:165-202), causal={int(causal)}")
 
 
 def reference_arm(args, wl):
@@ -139,7 +151,7 @@ def reference_arm(args, wl):
         t_tot += dt
         f_tot += fl
     tf = f_tot / t_tot * 1e-12
-    sample = f"{rows} query rows x {N} keys of one (b,h) slice per step, d={d}, fp32, causal={int(causal)}"
+    sample = sample_text(rows, N, d, causal) + " per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": tf, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": t_tot / steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -317,11 +329,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rows, run = cpu_attention_sample(B, H, N, d, causal, 12.0, threads)
-        dt, fl = run(rows)
+        sample, run = cpu_attention_sample(B, H, N, d, causal, 12.0, threads)
+        dt, fl = run(sample)
         cpu = {"value": fl / dt * 1e-12, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{rows} query rows x {N} keys of one (b,h) slice, d={d}, fp32 naive softmax(QK^T)V "
-                         f"(oracle port of main.cu:165-202), {dt:.1f} s"}
+               "sample": sample_text(sample, N, d, causal) + f", {dt:.1f} s"}
 
     if rank == 0:
         line = {

@@ -122,6 +122,9 @@ def test_large_score_range_exercises_lazy_rescale(fa):
     ramp = (1.0 + 6.0 * np.arange(N, dtype=np.float32) / N)[None, None, :, None]
     k = (k * ramp).astype(np.float32)
     k = torch.from_numpy(k).to(torch.bfloat16).float().numpy()        # keep inputs bf16-exact
+    # scores this peaked make the softmax nearly one-hot, so P's bf16 rounding (2^-9 relative) no longer
+    # averages out over the keys; |V| <= 0.25 keeps that term plus the output half-ulp inside the 2e-3 gate
+    v = v * 0.5
     o, lse, l, m = _run(fa, q, k, v, torch.bfloat16, False)
     o_ref, lse_ref, l_ref, m_ref = oracle.attention(q, k, v)
     _check(o, lse, o_ref, lse_ref)
