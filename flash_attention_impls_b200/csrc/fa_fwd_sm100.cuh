@@ -77,6 +77,33 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2(float2 v) { return pack2<kBF16>(v.x, v.y); }
+
+// 2^x for a pair of inputs on the FMA/ALU pipes (no MUFU): Cody-Waite split x = floor(x) + f,
+// degree-3 minimax polynomial for 2^f on [0,1) (max relative error 8.8e-5, well under the 2^-9 /
+// 2^-11 resolution of the bf16 / fp16 P it feeds), floor(x) added straight into the exponent field.
+// Used for a fixed fraction of every score row so that the 16/clk/SM MUFU.EX2 rate stops being the
+// bound (at d=128 the MMAs of one K/V tile take exactly as many cycles as its 16384 MUFU.EX2).
+__device__ __forceinline__ float2 ex2_emulated(float2 x) {
+  x.x = fmaxf(x.x, -127.f);
+  x.y = fmaxf(x.y, -127.f);
+  const float2 r = __fadd2_rd(x, make_float2(12582912.f, 12582912.f));     // 1.5*2^23 + floor(x)
+  const float2 fl = __fadd2_rn(r, make_float2(-12582912.f, -12582912.f));  // floor(x), exact
+  const float2 f = __ffma2_rn(fl, make_float2(-1.f, -1.f), x);             // x - floor(x) in [0,1)
+  float2 p = __ffma2_rn(f, make_float2(0.077119089663028717f, 0.077119089663028717f),
+                        make_float2(0.227564394474029541f, 0.227564394474029541f));
+  p = __ffma2_rn(p, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
+  p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+  p.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23));
+  p.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23));
+  return p;
+}
+
+#ifndef FA_EMU_PAIRS_OF_4
+#define FA_EMU_PAIRS_OF_4 0   // of every 4 score pairs, this many take the polynomial path
+#endif
+
 template <int D, bool kBF16, bool kCausal>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -96,11 +123,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // barrier slots (8 bytes each)
   const uint32_t bar_q_full = bars;                        // [2]
   const uint32_t bar_s_full = bars + 16;                   // [2]  MMA -> softmax
-  const uint32_t bar_p_full = bars + 32;                   // [2]  softmax -> MMA (128 arrivals)
-  const uint32_t bar_o_full = bars + 48;                   // [2]  MMA -> softmax (PV done)
-  const uint32_t bar_kv_full = bars + 64;                  // [kStages]
-  const uint32_t bar_kv_empty = bars + 64 + 8 * kStages;   // [kStages]
-  const uint32_t tmem_slot = bars + 64 + 16 * kStages;     // u32 written by tcgen05.alloc
+  const uint32_t bar_o_full = bars + 32;                   // [2]  MMA -> softmax (PV done)
+  const uint32_t bar_p_full = bars + 48;                   // [2 tiles][2 halves] softmax -> MMA (128 arrivals)
+  const uint32_t bar_kv_full = bars + 80;                  // [kStages]
+  const uint32_t bar_kv_empty = bars + 80 + 8 * kStages;   // [kStages]
+  const uint32_t tmem_slot = bars + 80 + 16 * kStages;     // u32 written by tcgen05.alloc
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,7 +163,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_q_full + 8 * i, 1);
       mbar_init(bar_s_full + 8 * i, 1);
-      mbar_init(bar_p_full + 8 * i, 128);
+      mbar_init(bar_p_full + 16 * i, 128);
+      mbar_init(bar_p_full + 16 * i + 8, 128);
       mbar_init(bar_o_full + 8 * i, 1);
     }
     for (int s = 0; s < kStages; ++s) {
@@ -196,14 +224,21 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     a.idesc_qk, k > 0 ? 1u : 0u);
           }
         };
-        auto issue_pv = [&](int i, int stage, bool acc) {
+        // O_i += P_i V_j, issued in two halves of 64 keys: the first half starts as soon as the softmax
+        // warpgroup has published the first 64 columns of P, while it is still exponentiating the rest.
+        auto issue_pv = [&](int i, int stage, bool acc, uint32_t parity) {
           const uint32_t b_base = sKV + stage * kTileBytes;
           const uint32_t p_tmem = tmem_base + i * kBlockN;           // P aliases S_i
           const uint32_t d_tmem = tmem_base + 2 * kBlockN + i * D;   // O_i
 #pragma unroll
-          for (int k = 0; k < kBlockN / 16; ++k) {
-            umma_ts(d_tmem, p_tmem + k * 8, umma_desc(a.desc_hi_v, b_base + k * 16 * 128), a.idesc_pv,
-                    (acc || k > 0) ? 1u : 0u);
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar_p_full + 16 * i + 8 * h, parity, 212 + 2 * i + h);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 4 * h; k < 4 * h + 4; ++k) {
+              umma_ts(d_tmem, p_tmem + k * 8, umma_desc(a.desc_hi_v, b_base + k * 16 * 128), a.idesc_pv,
+                      (acc || k > 0) ? 1u : 0u);
+            }
           }
         };
         auto stage_of = [&](int it) { return it % kStages; };
@@ -232,9 +267,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(bar_kv_full + 8 * stage_of(it_v), phase_of(it_v), 210);
           if (has_next) mbar_wait(bar_kv_full + 8 * stage_of(it_k), phase_of(it_k), 211);
           if (j < n_t0) {
-            mbar_wait(bar_p_full, j & 1, 212);
-            tc_fence_after();
-            issue_pv(0, stage_of(it_v), j > 0);
+            issue_pv(0, stage_of(it_v), j > 0, j & 1);
             umma_commit(bar_o_full);
           }
           if (j + 1 < n_t0) {
@@ -242,9 +275,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_commit(bar_s_full);
           }
           if (j < n_t1) {
-            mbar_wait(bar_p_full + 8, j & 1, 213);
-            tc_fence_after();
-            issue_pv(1, stage_of(it_v), j > 0);
+            issue_pv(1, stage_of(it_v), j > 0, j & 1);
             umma_commit(bar_o_full + 8);
           }
           umma_commit(bar_kv_empty + 8 * stage_of(it_v));
@@ -269,7 +300,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tS = tmem_base + lane_addr + i * kBlockN;
     const uint32_t tO = tmem_base + lane_addr + 2 * kBlockN + i * D;
     const uint32_t b_s_full = bar_s_full + 8 * i;
-    const uint32_t b_p_full = bar_p_full + 8 * i;
+    const uint32_t b_p_full = bar_p_full + 16 * i;
     const uint32_t b_o_full = bar_o_full + 8 * i;
 
     const float c = a.scale_log2;
@@ -331,23 +362,35 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
 
-      float lsum = 0.f;
+      // p = 2^(s*c - m_ref) with packed (2-wide) fp32 math; FA_EMU_PAIRS_OF_4 of every 4 pairs take the
+      // polynomial path, the rest MUFU.EX2.  P is published to the MMA warp in two halves of 64 keys.
+      const float2 c2 = make_float2(c, c), neg_m2 = make_float2(neg_m, neg_m);
+      float2 lsum2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint32_t pk[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[q][2 * k]), c, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sr[q][2 * k + 1]), c, neg_m));
-          lsum += p0 + p1;
-          pk[k] = pack2<kBF16>(p0, p1);
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[q][2 * k]), __uint_as_float(sr[q][2 * k + 1])),
+                                      c2, neg_m2);
+          float2 pv;
+          if ((k & 3) < FA_EMU_PAIRS_OF_4) {
+            pv = ex2_emulated(x);
+          } else {
+            pv.x = ex2_approx(x.x);
+            pv.y = ex2_approx(x.y);
+          }
+          lsum2 = __fadd2_rn(lsum2, pv);
+          pk[k] = pack2<kBF16>(pv);
         }
         tmem_st16(tS + q * 16, pk);   // P(16-bit) over the first 64 columns of S
+        if (q & 1) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(b_p_full + 8 * (q >> 1));
+        }
       }
-      l += lsum;
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(b_p_full);
+      l += lsum2.x + lsum2.y;
     }
 
     // ---- epilogue: O_i / l -> 16-bit -> swizzled smem (dead Q tile) -> TMA store
@@ -356,6 +399,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(b_o_full, (n_i - 1) & 1, 320 + i);
         tc_fence_after();
       }
+      if (limit < 0) l = 0.f;   // row sees no key at all: the polynomial exp2 returns 2^-127, not 0
       const float inv_l = (l > 0.f) ? (1.f / l) : 0.f;
       const uint32_t sO = sQ + i * kTileBytes;
 #pragma unroll
