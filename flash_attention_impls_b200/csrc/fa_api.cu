@@ -106,7 +106,31 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
     if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
     configured.fetch_or(bit);
   }
+#ifdef FA_TRACE
+  // bring-up only: dump the clock64 timeline of CTA 0 to $FA_B200_TRACE after a synchronous run
+  fa::FwdArgs targs = args;
+  static long long* trace_dev = nullptr;
+  const char* trace_path = getenv("FA_B200_TRACE");
+  if (trace_path) {
+    if (!trace_dev) cudaMalloc(&trace_dev, 32 * 16 * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, 32 * 16 * sizeof(long long), stream);
+    targs.trace = trace_dev;
+  }
+  kern<<<dim3((unsigned)grid), dim3(fa::kNumThreads), smem, stream>>>(tq, tk, tv, to, targs);
+  if (trace_path) {
+    long long h[32 * 16];
+    cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int j = 0; j < 32; ++j) {
+        for (int ev = 0; ev < 16; ++ev) fprintf(f, "%lld ", h[j * 16 + ev]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+#else
   kern<<<dim3((unsigned)grid), dim3(fa::kNumThreads), smem, stream>>>(tq, tk, tv, to, args);
+#endif
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1);

@@ -39,7 +39,17 @@ struct FwdArgs {
   unsigned long long desc_hi_qk;  // K-major 128B-swizzle descriptor bits (Q, K)
   unsigned long long desc_hi_v;   // MN-major 128B-swizzle descriptor bits (V)
   unsigned int idesc_qk, idesc_pv;
+  long long* trace;   // bring-up only (-DFA_TRACE): clock64 timeline of CTA 0, see tools/trace_report.py
 };
+
+#ifdef FA_TRACE
+#define FA_TRACE_EV(j, ev)                                                          \
+  do {                                                                              \
+    if (blockIdx.x == 0 && a.trace != nullptr && (j) < 32) a.trace[(j) * 16 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define FA_TRACE_EV(j, ev) do {} while (0)
+#endif
 
 constexpr int kBlockM = 128;        // rows per Q tile
 constexpr int kBlockN = 128;        // keys per K/V tile
@@ -81,19 +91,20 @@ template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float2 v) { return pack2<kBF16>(v.x, v.y); }
 
 // 2^x for a pair of inputs on the FMA/ALU pipes (no MUFU): Cody-Waite split x = floor(x) + f,
-// degree-3 minimax polynomial for 2^f on [0,1) (max relative error 8.8e-5, well under the 2^-9 /
-// 2^-11 resolution of the bf16 / fp16 P it feeds), floor(x) added straight into the exponent field.
-// Used for a fixed fraction of every score row so that the 16/clk/SM MUFU.EX2 rate stops being the
-// bound (at d=128 the MMAs of one K/V tile take exactly as many cycles as its 16384 MUFU.EX2).
+// degree-4 minimax polynomial for 2^f on [0,1) (max relative error 3e-6 with p(0) = 1 exactly; fitted by
+// linear programming on the relative error), floor(x) added straight into the exponent
+// field.  Used for a fixed fraction of every score row to take load off the 16/clk/SM MUFU.EX2 unit
+// (at d=128 the MMAs of one K/V tile take exactly as many cycles as its 16384 MUFU.EX2).
 __device__ __forceinline__ float2 ex2_emulated(float2 x) {
   x.x = fmaxf(x.x, -127.f);
   x.y = fmaxf(x.y, -127.f);
   const float2 r = __fadd2_rd(x, make_float2(12582912.f, 12582912.f));     // 1.5*2^23 + floor(x)
   const float2 fl = __fadd2_rn(r, make_float2(-12582912.f, -12582912.f));  // floor(x), exact
   const float2 f = __ffma2_rn(fl, make_float2(-1.f, -1.f), x);             // x - floor(x) in [0,1)
-  float2 p = __ffma2_rn(f, make_float2(0.077119089663028717f, 0.077119089663028717f),
-                        make_float2(0.227564394474029541f, 0.227564394474029541f));
-  p = __ffma2_rn(p, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
+  float2 p = __ffma2_rn(f, make_float2(0.013425154611468315f, 0.013425154611468315f),
+                        make_float2(0.0522453747689724f, 0.0522453747689724f));
+  p = __ffma2_rn(p, f, make_float2(0.24127855896949768f, 0.24127855896949768f));
+  p = __ffma2_rn(p, f, make_float2(0.6930451393127441f, 0.6930451393127441f));
   p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
   p.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23));
   p.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23));
@@ -101,7 +112,7 @@ __device__ __forceinline__ float2 ex2_emulated(float2 x) {
 }
 
 #ifndef FA_EMU_PAIRS_OF_4
-#define FA_EMU_PAIRS_OF_4 0   // of every 4 score pairs, this many take the polynomial path
+#define FA_EMU_PAIRS_OF_4 1   // of every 4 score pairs, this many take the polynomial path
 #endif
 
 template <int D, bool kBF16, bool kCausal>
@@ -212,81 +223,93 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
     } else if (warp == 9) {
       // =========================== MMA issuer ===========================
-      if (lane == 0) {
-        auto issue_qk = [&](int i, int stage) {
-          const uint32_t a_base = sQ + i * kTileBytes;
-          const uint32_t b_base = sKV + stage * kTileBytes;
-          const uint32_t d_tmem = tmem_base + i * kBlockN;
+      // The whole warp runs the (uniform) control flow and the barrier waits; one elected lane issues
+      // the tcgen05.mma / tcgen05.commit instructions.  Keeping the flow warp-uniform lets the compiler
+      // hold descriptors in uniform registers: the issue cost per MMA must stay well under the 64
+      // cycles one 128x128x16 MMA takes on the tensor pipe.
+      const uint32_t hi_qk = uint32_t(a.desc_hi_qk >> 32), hi_v = uint32_t(a.desc_hi_v >> 32);
+      const uint32_t lo_qk = uint32_t(a.desc_hi_qk), lo_v = uint32_t(a.desc_hi_v);
+      const uint32_t idesc_qk = a.idesc_qk, idesc_pv = a.idesc_pv;
+      int trace_j = 0;
+      (void)trace_j;
+      // S_i = Q_i K^T, then signal `bar_done` (and optionally release the K stage) when it has landed
+      auto issue_qk = [&](int i, int stage, uint32_t bar_done, uint32_t bar_release) {
+        const uint32_t a_lo = lo_qk | ((sQ + i * kTileBytes) >> 4);
+        const uint32_t b_lo = lo_qk | ((sKV + stage * kTileBytes) >> 4);
+        const uint32_t d_tmem = tmem_base + i * kBlockN;
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = (k / 4) * kBoxBytes + (k % 4) * 32;
-            umma_ss(d_tmem, umma_desc(a.desc_hi_qk, a_base + off), umma_desc(a.desc_hi_qk, b_base + off),
-                    a.idesc_qk, k > 0 ? 1u : 0u);
+            const uint32_t off = ((k / 4) * kBoxBytes + (k % 4) * 32) >> 4;
+            umma_ss(d_tmem, a_lo + off, hi_qk, b_lo + off, hi_qk, idesc_qk, k > 0 ? 1u : 0u);
           }
-        };
-        // O_i += P_i V_j, issued in two halves of 64 keys: the first half starts as soon as the softmax
-        // warpgroup has published the first 64 columns of P, while it is still exponentiating the rest.
-        auto issue_pv = [&](int i, int stage, bool acc, uint32_t parity) {
-          const uint32_t b_base = sKV + stage * kTileBytes;
-          const uint32_t p_tmem = tmem_base + i * kBlockN;           // P aliases S_i
-          const uint32_t d_tmem = tmem_base + 2 * kBlockN + i * D;   // O_i
+          umma_commit(bar_done);
+          if (bar_release) umma_commit(bar_release);
+        }
+        __syncwarp();
+      };
+      // O_i += P_i V_j, issued in two halves of 64 keys: the first half starts as soon as the softmax
+      // warpgroup has published the first 64 columns of P, while it is still exponentiating the rest.
+      auto issue_pv = [&](int i, int stage, bool acc, uint32_t parity, uint32_t bar_done, uint32_t bar_release) {
+        const uint32_t b_lo = lo_v | ((sKV + stage * kTileBytes) >> 4);
+        const uint32_t p_tmem = tmem_base + i * kBlockN;           // P aliases S_i
+        const uint32_t d_tmem = tmem_base + 2 * kBlockN + i * D;   // O_i
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(bar_p_full + 16 * i + 8 * h, parity, 212 + 2 * i + h);
-            tc_fence_after();
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar_p_full + 16 * i + 8 * h, parity, 212 + 2 * i + h);
+          tc_fence_after();
+          if (lane == 0) FA_TRACE_EV(trace_j, 8 + 3 * i + h);
+          if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 4 * h; k < 4 * h + 4; ++k) {
-              umma_ts(d_tmem, p_tmem + k * 8, umma_desc(a.desc_hi_v, b_base + k * 16 * 128), a.idesc_pv,
-                      (acc || k > 0) ? 1u : 0u);
+            for (int k = 4 * h; k < 4 * h + 4; ++k)
+              umma_ts(d_tmem, p_tmem + k * 8, b_lo + k * (16 * 128 / 16), hi_v, idesc_pv, (acc || k > 0) ? 1u : 0u);
+            if (h == 1) {
+              umma_commit(bar_done);
+              if (bar_release) umma_commit(bar_release);
             }
           }
-        };
-        auto stage_of = [&](int it) { return it % kStages; };
-        auto phase_of = [&](int it) { return uint32_t((it / kStages) & 1); };
-
-        if (n_max > 0) {
-          // S_i(0) = Q_i K_0^T
-          mbar_wait(bar_kv_full + 8 * stage_of(0), phase_of(0), 200);
-          if (n_t0 > 0) {
-            mbar_wait(bar_q_full, 0, 201);
-            tc_fence_after();
-            issue_qk(0, stage_of(0));
-            umma_commit(bar_s_full);
-          }
-          if (n_t1 > 0) {
-            mbar_wait(bar_q_full + 8, 0, 202);
-            tc_fence_after();
-            issue_qk(1, stage_of(0));
-            umma_commit(bar_s_full + 8);
-          }
-          umma_commit(bar_kv_empty + 8 * stage_of(0));
+          __syncwarp();
         }
-        for (int j = 0; j < n_max; ++j) {
-          const int it_v = 2 * j + 1, it_k = 2 * j + 2;
-          const bool has_next = (j + 1 < n_max);
-          mbar_wait(bar_kv_full + 8 * stage_of(it_v), phase_of(it_v), 210);
-          if (has_next) mbar_wait(bar_kv_full + 8 * stage_of(it_k), phase_of(it_k), 211);
-          if (j < n_t0) {
-            issue_pv(0, stage_of(it_v), j > 0, j & 1);
-            umma_commit(bar_o_full);
-          }
-          if (j + 1 < n_t0) {
-            issue_qk(0, stage_of(it_k));
-            umma_commit(bar_s_full);
-          }
-          if (j < n_t1) {
-            issue_pv(1, stage_of(it_v), j > 0, j & 1);
-            umma_commit(bar_o_full + 8);
-          }
-          umma_commit(bar_kv_empty + 8 * stage_of(it_v));
-          if (j + 1 < n_t1) {
-            issue_qk(1, stage_of(it_k));
-            umma_commit(bar_s_full + 8);
-          }
-          if (has_next) umma_commit(bar_kv_empty + 8 * stage_of(it_k));
+      };
+      auto stage_of = [&](int it) { return it % kStages; };
+      auto phase_of = [&](int it) { return uint32_t((it / kStages) & 1); };
+
+      if (n_max > 0) {
+        // S_i(0) = Q_i K_0^T
+        mbar_wait(bar_kv_full + 8 * stage_of(0), phase_of(0), 200);
+        const uint32_t rel = bar_kv_empty + 8 * stage_of(0);
+        if (n_t0 > 0) {
+          mbar_wait(bar_q_full, 0, 201);
+          tc_fence_after();
+          issue_qk(0, stage_of(0), bar_s_full, n_t1 > 0 ? 0u : rel);
+        }
+        if (n_t1 > 0) {
+          mbar_wait(bar_q_full + 8, 0, 202);
+          tc_fence_after();
+          issue_qk(1, stage_of(0), bar_s_full + 8, rel);
         }
       }
-      __syncwarp();
+      for (int j = 0; j < n_max; ++j) {
+        const int it_v = 2 * j + 1, it_k = 2 * j + 2;
+        const bool has_next = (j + 1 < n_max);
+        mbar_wait(bar_kv_full + 8 * stage_of(it_v), phase_of(it_v), 210);
+        if (has_next) mbar_wait(bar_kv_full + 8 * stage_of(it_k), phase_of(it_k), 211);
+        trace_j = j;
+        const uint32_t rel_v = bar_kv_empty + 8 * stage_of(it_v);
+        const uint32_t rel_k = bar_kv_empty + 8 * stage_of(it_k);
+        // n_t1 >= n_t0 whenever both tiles exist (the second tile sits lower in the causal triangle);
+        // tile 1 is absent (n_t1 == 0) only for a ragged last block.
+        if (j < n_t0) issue_pv(0, stage_of(it_v), j > 0, j & 1, bar_o_full, j < n_t1 ? 0u : rel_v);
+        if (j + 1 < n_t0) {
+          if (lane == 0) FA_TRACE_EV(j, 10);
+          issue_qk(0, stage_of(it_k), bar_s_full, j + 1 < n_t1 ? 0u : rel_k);
+        }
+        if (j < n_t1) issue_pv(1, stage_of(it_v), j > 0, j & 1, bar_o_full + 8, rel_v);
+        if (j + 1 < n_t1) {
+          if (lane == 0) FA_TRACE_EV(j, 13);
+          issue_qk(1, stage_of(it_k), bar_s_full + 8, rel_k);
+        }
+      }
     }
   } else {
     // =========================== softmax warpgroups ===========================
@@ -315,10 +338,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < n_i; ++j) {
       mbar_wait(b_s_full, j & 1, 300 + i);
       tc_fence_after();
+      if (row_in_tile == 0) FA_TRACE_EV(j, 4 * i + 0);
       uint32_t sr[4][32];
 #pragma unroll
       for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, sr[q]);
       tmem_wait_ld();
+      if (row_in_tile == 0) FA_TRACE_EV(j, 4 * i + 1);
 
       // masking: key index > limit -> -inf (diagonal tiles of causal runs, ragged last tile)
       const int lim_local = limit - j * kBlockN;
@@ -330,11 +355,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (q * 32 + k > lim_local) sr[q][k] = 0xff800000u;  // -inf
       }
 
-      float mx = -INFINITY;
+      // row max with four independent chains (a single chain of 64 dependent FMNMX3 costs ~4 clk each)
+      float mxp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(sr[q][k]));
+        for (int k = 0; k < 32; k += 8)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            mxp[u] = fmaxf(mxp[u], fmaxf(__uint_as_float(sr[q][k + 2 * u]), __uint_as_float(sr[q][k + 2 * u + 1])));
+      const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
       const float m_new = fmaxf(m_true, mx * c);
       m_true = m_new;
 
@@ -365,7 +395,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // p = 2^(s*c - m_ref) with packed (2-wide) fp32 math; FA_EMU_PAIRS_OF_4 of every 4 pairs take the
       // polynomial path, the rest MUFU.EX2.  P is published to the MMA warp in two halves of 64 keys.
       const float2 c2 = make_float2(c, c), neg_m2 = make_float2(neg_m, neg_m);
-      float2 lsum2 = make_float2(0.f, 0.f);
+      float2 lsum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint32_t pk[16];
@@ -380,7 +410,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             pv.x = ex2_approx(x.x);
             pv.y = ex2_approx(x.y);
           }
-          lsum2 = __fadd2_rn(lsum2, pv);
+          lsum2[k & 3] = __fadd2_rn(lsum2[k & 3], pv);
           pk[k] = pack2<kBF16>(pv);
         }
         tmem_st16(tS + q * 16, pk);   // P(16-bit) over the first 64 columns of S
@@ -388,9 +418,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(b_p_full + 8 * (q >> 1));
+          if (row_in_tile == 0) FA_TRACE_EV(j, 4 * i + 2 + (q >> 1));
         }
       }
-      l += lsum2.x + lsum2.y;
+      const float2 lsum = __fadd2_rn(__fadd2_rn(lsum2[0], lsum2[1]), __fadd2_rn(lsum2[2], lsum2[3]));
+      l += lsum.x + lsum.y;
     }
 
     // ---- epilogue: O_i / l -> 16-bit -> swizzled smem (dead Q tile) -> TMA store
