@@ -3,9 +3,10 @@ multi-GPU code at all; both modes are new work named by BASELINE.json's north_st
 
 * (batch, head) sharding — `[B,H,N,d]` is contiguous in b*H+h (reference: flashAttention.cu:30), the
   (b,h) slices are independent, so rank g of P simply owns a contiguous range of them.  No collective.
-* ring attention — the sequence is split over the ranks; K/V blocks circulate with NCCL send/recv
-  (torch.distributed P2P over NVLink) while each rank runs the local kernel on the block it holds, and the
-  per-block partials are merged with their logsumexp.  Causal runs use the zig-zag partition (rank r owns
+* ring attention — the sequence is split over the ranks; K/V blocks travel with NCCL send/recv
+  (torch.distributed P2P over NVLink/NVSwitch) while each rank runs the local kernel on the block it holds,
+  in ring order (step s uses the block of rank r-s), and the per-block partials are merged with their
+  logsumexp.  Causal runs use the zig-zag partition (rank r owns
   sequence chunks r and 2P-1-r) so that every rank does the same amount of work at every step.
 
 One process per GPU; the compute calls go to libfa_b200.so through `ops`.  The `backend` argument
@@ -70,16 +71,22 @@ class _CudaBackend:
         return ops.cast_output(o_acc, dtype)
 
 
-def _exchange(send_k, send_v, recv_k, recv_v, group, rank, world):
-    """Post the ring hop: send the resident K/V block to rank+1, receive the next one from rank-1."""
-    nxt, prv = (rank + 1) % world, (rank - 1) % world
-    g_nxt = dist.get_global_rank(group, nxt) if group is not None else nxt
-    g_prv = dist.get_global_rank(group, prv) if group is not None else prv
+def _post_block_exchange(k, v, recv_k, recv_v, step, group, rank, world):
+    """Post the transfers of ring step `step`: my own K/V block goes to the rank that needs it at that step,
+    (rank + step) mod P, and the block I need, the one owned by (rank - step) mod P, comes in.
+
+    Every GPU has full NVLink bandwidth to every peer through NVSwitch, so the block does not have to hop
+    around the ring: each owner sends it directly.  That removes the step-to-step dependency of a forwarding
+    ring: all P-1 exchanges are posted up front and run back to back on NCCL's stream while the kernels of
+    the earlier steps compute."""
+    dst, src = (rank + step) % world, (rank - step) % world
+    g_dst = dist.get_global_rank(group, dst) if group is not None else dst
+    g_src = dist.get_global_rank(group, src) if group is not None else src
     ops_ = [
-        dist.P2POp(dist.isend, send_k, g_nxt, group),
-        dist.P2POp(dist.irecv, recv_k, g_prv, group),
-        dist.P2POp(dist.isend, send_v, g_nxt, group),
-        dist.P2POp(dist.irecv, recv_v, g_prv, group),
+        dist.P2POp(dist.isend, k, g_dst, group),
+        dist.P2POp(dist.irecv, recv_k, g_src, group),
+        dist.P2POp(dist.isend, v, g_dst, group),
+        dist.P2POp(dist.irecv, recv_v, g_src, group),
     ]
     return dist.batch_isend_irecv(ops_)
 
@@ -93,8 +100,9 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
       causal:     the zig-zag partition (`zigzag_split`): local rows = [chunk r ; chunk 2P-1-r].
     Returns (O_local `[B,H,N_local,d]` in q.dtype, lse_local `[B,H,N_local]` fp32).
 
-    Step s (s = 0..P-1) works on the block that originated on rank (r - s) mod P while the block for
-    step s+1 is in flight.  With the zig-zag layout the causal structure per step is one of
+    Step s (s = 0..P-1) works on the block owned by rank (r - s) mod P; the P-1 remote blocks are fetched
+    with NCCL send/recv posted up front (see _post_block_exchange), so step s never waits on step s-1's
+    transfer.  With the zig-zag layout the causal structure per step is one of
       src == r : square causal on the local block
       src <  r : every local query row sees only the FIRST half of the visiting block (no mask)
       src >  r : only the SECOND half of the local query rows see the visiting block (no mask)
@@ -115,12 +123,17 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     o_part = torch.empty((B, H, Nl, d), dtype=q.dtype, device=q.device)
     lse_part = torch.empty((B, H, Nl), dtype=torch.float32, device=q.device)
 
-    cur_k, cur_v = k.contiguous(), v.contiguous()
-    nxt_k, nxt_v = torch.empty_like(cur_k), torch.empty_like(cur_v)
+    own_k, own_v = k.contiguous(), v.contiguous()
+    blocks = [(own_k, own_v)] + [(torch.empty_like(own_k), torch.empty_like(own_v)) for _ in range(world - 1)]
+    reqs = [None] + [_post_block_exchange(own_k, own_v, blocks[s][0], blocks[s][1], s, group, rank, world)
+                     for s in range(1, world)]
 
     for step in range(world):
         src = (rank - step) % world
-        reqs = _exchange(cur_k, cur_v, nxt_k, nxt_v, group, rank, world) if step + 1 < world else []
+        if step > 0:
+            for r_ in reqs[step]:
+                r_.wait()
+        cur_k, cur_v = blocks[step]
 
         if not causal or src == rank:
             be.attention(q, cur_k, cur_v, causal and src == rank, o_part, lse_part)
@@ -132,10 +145,5 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
             lse_part[:, :, :half].fill_(float("-inf"))
             be.attention(q[:, :, half:], cur_k, cur_v, False, o_part[:, :, half:], lse_part[:, :, half:])
         be.merge(o_acc, lse_acc, o_part, lse_part)
-
-        for r_ in reqs:
-            r_.wait()
-        cur_k, nxt_k = nxt_k, cur_k
-        cur_v, nxt_v = nxt_v, cur_v
 
     return be.finalize(o_acc, q.dtype), lse_acc
