@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -91,6 +92,7 @@ int check_device() {
   return FA_B200_OK;
 }
 
+
 template <int D, bool kBF16, bool kCausal>
 int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
            const fa::FwdArgs& args, long long grid, cudaStream_t stream) {
@@ -112,19 +114,24 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
   static long long* trace_dev = nullptr;
   const char* trace_path = getenv("FA_B200_TRACE");
   if (trace_path) {
-    if (!trace_dev) cudaMalloc(&trace_dev, 32 * 16 * sizeof(long long));
-    cudaMemsetAsync(trace_dev, 0, 32 * 16 * sizeof(long long), stream);
+    const size_t trace_n = 4096 + 160 * 40 * 2;
+    if (!trace_dev) cudaMalloc(&trace_dev, trace_n * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), stream);
     targs.trace = trace_dev;
   }
   kern<<<dim3((unsigned)grid), dim3(fa::kNumThreads), smem, stream>>>(tq, tk, tv, to, targs);
   if (trace_path) {
-    long long h[32 * 16];
+    static long long h[4096 + 160 * 40 * 2];
     cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
     if (FILE* f = fopen(trace_path, "w")) {
       for (int j = 0; j < 32; ++j) {
         for (int ev = 0; ev < 16; ++ev) fprintf(f, "%lld ", h[j * 16 + ev]);
         fprintf(f, "\n");
       }
+      fprintf(f, "#items cta t item globaltimer_ns\n");
+      for (int c = 0; c < 160; ++c)
+        for (int t = 0; t < 40; ++t)
+          if (h[4096 + (c * 40 + t) * 2]) fprintf(f, "I %d %d %lld %lld\n", c, t, h[4096 + (c * 40 + t) * 2] - 1, h[4096 + (c * 40 + t) * 2 + 1]);
       fclose(f);
     }
   }
@@ -189,6 +196,17 @@ int fa_b200_forward(const fa_b200_params* p) {
   a.Nkv = Nkv;
   a.causal_off = Nkv - Nq;
   a.num_q_blocks = (int)num_q_blocks;
+  a.num_items = (int)(BH * num_q_blocks);
+  a.num_bh = (int)BH;
+  {
+    // heads whose K and V (2 * N_kv * d * 2 bytes each) fit in about half of the 126 MB L2 together
+    const long long kv_bytes_per_head = 4LL * Nkv * d;
+    long long g = (64LL << 20) / (kv_bytes_per_head > 0 ? kv_bytes_per_head : 1);
+    g = std::max<long long>(1, std::min<long long>(g, BH));
+    a.group_heads = (int)env_u64("FA_B200_GROUP_HEADS", (unsigned long long)g);
+    if (a.group_heads < 1) a.group_heads = 1;
+    if (a.group_heads > BH) a.group_heads = (int)BH;
+  }
   a.scale_log2 = scale * 1.4426950408889634f;
   a.stat_stride_bh = ss;
   const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;
@@ -206,6 +224,8 @@ int fa_b200_forward(const fa_b200_params* p) {
   a.idesc_pv = (unsigned)env_u64("FA_B200_IDESC_PV", a.idesc_pv);
 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
+  // one CTA per work item; resident CTAs steal the not-yet-launched ones (cluster launch control), so the
+  // kernel behaves as a persistent kernel with a dynamic hardware scheduler
   const long long grid = BH * num_q_blocks;
   const bool bf16 = p->dtype == FA_B200_BF16;
   const bool causal = p->causal != 0;

@@ -6,18 +6,25 @@
 //   code/triton_fa2/FA2-triton.py:25-93                (Triton FA2 fwd; causal rule :70-73)
 // with a from-scratch design:
 //
-//   CTA = 384 threads, one CTA per SM, two 128-row Q tiles per CTA (ping-pong).
-//     warps 0-3  : softmax warpgroup for Q tile 0   (one thread owns one score row, no shuffles)
-//     warps 4-7  : softmax warpgroup for Q tile 1
-//     warp  8    : TMA producer  (Q once, then K_j / V_j through a multi-stage mbarrier ring)
-//     warp  9    : tcgen05.mma issuer (one thread): S_i = Q_i K_j^T -> TMEM, O_i += P_i V_j
-//     warp  10   : TMEM allocator / deallocator
+//   Persistent kernel with a hardware tile scheduler: the grid has one CTA per work item, but a running CTA
+//   (512 threads, one per SM) keeps its TMEM, barriers and pipelines and steals the next not-yet-launched
+//   blockIdx through cluster launch control (clusterlaunchcontrol.try_cancel), so scheduling is dynamic
+//   (longest-first for causal) without any global counter.  A work item is 256 query rows of one (b,h): two
+//   128-row Q tiles that ping-pong on the tensor pipe; the item list is head-major (causal: longest
+//   q-blocks of a head first) so resident CTAs share K/V in L2.
+//     warps 0-3   : softmax warpgroup for Q tile 0   (one thread owns one score row, no shuffles)
+//     warps 4-7   : softmax warpgroup for Q tile 1
+//     warps 8-11  : correction/epilogue warpgroup: O_i * (1/l) -> 16-bit -> swizzled smem -> TMA store,
+//                   overlapped with the next work item's MMAs and softmax
+//     warp  12    : TMA producer  (Q per item, K_j / V_j through a multi-stage mbarrier ring that runs
+//                   across items, so the next item's first tiles are prefetched)
+//     warp  13    : tcgen05.mma issuer (one elected lane): S_i = Q_i K_j^T -> TMEM, O_i += P_i V_j
+//     warp  14    : TMEM allocator / deallocator
 //   TMEM (512 columns): S0 | S1 | O0 | O1, fp32.  P (bf16/fp16) is written back over the first
 //   columns of its S tile and consumed by the PV MMA directly from TMEM (A-operand in TMEM).
 //   Online softmax runs in the log2 domain with a lazily updated reference max: O and l are only
 //   rescaled when the true row max has moved more than 2^8 above the reference max.
-//   Epilogue: O/l -> 16-bit -> swizzled smem (re-using the dead Q tile) -> TMA store; the
-//   logsumexp (and the reference's l, m) are written with coalesced fp32 stores.
+//   The logsumexp (and the reference's l, m) are written with coalesced fp32 stores.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -34,6 +41,9 @@ struct FwdArgs {
   int Nq, Nkv;
   int causal_off;   // Nkv - Nq (bottom-right aligned causal; 0 for the square case)
   int num_q_blocks; // ceil(Nq / 256)
+  int num_items;    // B*H*num_q_blocks work items (= grid size; later ones are stolen by resident CTAs)
+  int num_bh;       // B*H
+  int group_heads;  // causal item ordering: heads per L2-sized group (see get_item)
   float scale_log2; // softmax_scale * log2(e)
   long long stat_stride_bh;
   unsigned long long desc_hi_qk;  // K-major 128B-swizzle descriptor bits (Q, K)
@@ -53,7 +63,7 @@ struct FwdArgs {
 
 constexpr int kBlockM = 128;        // rows per Q tile
 constexpr int kBlockN = 128;        // keys per K/V tile
-constexpr int kNumThreads = 384;
+constexpr int kNumThreads = 512;
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum on sm_100
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -62,12 +72,13 @@ struct FwdTraits {
   static constexpr int kTileBytes = kBlockN * D * 2;       // one Q/K/V/O tile, 16-bit elements
   static constexpr int kBoxBytes = 128 * 64 * 2;           // one 64-column TMA box (128B swizzle)
   static constexpr int kNumBoxes = D / 64;
-  static constexpr int kBarrierBytes = 1024;
-  static constexpr int kStagesMax = (kSmemLimit - 1024 /*align slack*/ - kBarrierBytes - 2 * kTileBytes) / kTileBytes;
+  static constexpr int kAuxBytes = 3072;                   // mbarriers (512 B) + 1/l hand-off (1 KB) + slack
+  // shared memory: Q0 | Q1 | O staging (one tile) | K/V ring | aux
+  static constexpr int kStagesMax = (kSmemLimit - kAuxBytes - 3 * kTileBytes) / kTileBytes;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
-  static constexpr int kSmemBytes = 1024 + (2 + kStages) * kTileBytes + kBarrierBytes;
+  static constexpr int kSmemBytes = (3 + kStages) * kTileBytes + kAuxBytes;
   static_assert(D == 64 || D == 128, "head_dim must be 64 or 128");
-  static_assert(kStages >= 2, "need at least a double-buffered K/V ring");
+  static_assert(kStages >= 3, "K/V ring too shallow");
 };
 
 template <bool kBF16>
@@ -115,6 +126,52 @@ __device__ __forceinline__ float2 ex2_emulated(float2 x) {
 #define FA_EMU_PAIRS_OF_4 1   // of every 4 score pairs, this many take the polynomial path
 #endif
 
+// One work item = 256 query rows of one (b,h).  Every role walks the same deterministic item list.
+struct WorkItem {
+  int bh, q0, n_t0, n_t1, n_max;
+  bool valid0, valid1;   // tile has at least one real query row
+};
+
+template <bool kCausal>
+__device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
+  WorkItem it;
+  int qb;
+  if (kCausal) {
+    // Causal items differ in length (q-block qb visits qb+1.. K/V tiles), so the list is ordered
+    // longest-first, but only within groups of `group_heads` heads whose K/V fit the L2 together:
+    // group-major, then q-block descending, then head.  This keeps the K/V of the running CTAs shared in
+    // L2 and leaves only the shortest items of the last group for the tail of the launch.
+    const int per_group = a.group_heads * a.num_q_blocks;
+    const int g = w / per_group;
+    const int r = w - g * per_group;
+    const int heads = min(a.group_heads, a.num_bh - g * a.group_heads);
+    const int qi = r / heads;
+    it.bh = g * a.group_heads + (r - qi * heads);
+    qb = a.num_q_blocks - 1 - qi;
+  } else {
+    it.bh = w / a.num_q_blocks;
+    qb = w - it.bh * a.num_q_blocks;
+  }
+  it.q0 = qb * 2 * kBlockM;
+  const int n_kv_tiles = (a.Nkv + kBlockN - 1) / kBlockN;
+  // number of K/V tiles each Q tile visits (masked tiles above the diagonal are skipped)
+  auto tiles_for = [&](int r0) {
+    int n = (r0 < a.Nq) ? n_kv_tiles : 0;
+    if (kCausal && n > 0) {
+      const int last_row = min(r0 + kBlockM - 1, a.Nq - 1);
+      const int last_col = last_row + a.causal_off;   // largest visible key index
+      n = last_col < 0 ? 0 : min(n, last_col / kBlockN + 1);
+    }
+    return n;
+  };
+  it.n_t0 = tiles_for(it.q0);
+  it.n_t1 = tiles_for(it.q0 + kBlockM);
+  it.n_max = max(it.n_t0, it.n_t1);
+  it.valid0 = it.q0 < a.Nq;
+  it.valid1 = it.q0 + kBlockM < a.Nq;
+  return it;
+}
+
 template <int D, bool kBF16, bool kCausal>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -126,65 +183,76 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t kBoxBytes = T::kBoxBytes;
   constexpr int kNumBoxes = T::kNumBoxes;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1 KB alignment
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();   // 128B swizzle atoms need 1 KB alignment
   const uint32_t sQ = smem_base;
-  const uint32_t sKV = smem_base + 2 * kTileBytes;
-  const uint32_t bars = smem_base + (2 + kStages) * kTileBytes;
+  const uint32_t sO = smem_base + 2 * kTileBytes;          // epilogue staging, one tile
+  const uint32_t sKV = smem_base + 3 * kTileBytes;
+  const uint32_t bars = smem_base + (3 + kStages) * kTileBytes;
   // barrier slots (8 bytes each)
-  const uint32_t bar_q_full = bars;                        // [2]
-  const uint32_t bar_s_full = bars + 16;                   // [2]  MMA -> softmax
-  const uint32_t bar_o_full = bars + 32;                   // [2]  MMA -> softmax (PV done)
-  const uint32_t bar_p_full = bars + 48;                   // [2 tiles][2 halves] softmax -> MMA (128 arrivals)
-  const uint32_t bar_kv_full = bars + 80;                  // [kStages]
-  const uint32_t bar_kv_empty = bars + 80 + 8 * kStages;   // [kStages]
-  const uint32_t tmem_slot = bars + 80 + 16 * kStages;     // u32 written by tcgen05.alloc
+  const uint32_t bar_q_full = bars;                        // [2]  TMA -> MMA
+  const uint32_t bar_q_empty = bars + 16;                  // [2]  MMA -> TMA (all QK^T of the item issued+done)
+  const uint32_t bar_s_full = bars + 32;                   // [2]  MMA -> softmax
+  const uint32_t bar_o_full = bars + 48;                   // [2]  MMA -> softmax/epilogue (a PV has landed)
+  const uint32_t bar_o_free = bars + 64;                   // [2]  epilogue -> MMA (O_i read out of TMEM)
+  const uint32_t bar_ep_full = bars + 80;                  // [2]  softmax -> epilogue (1/l published)
+  const uint32_t bar_ep_empty = bars + 96;                 // [2]  epilogue -> softmax (1/l slot consumed)
+  const uint32_t bar_p_full = bars + 112;                  // [2 tiles][2 halves] softmax -> MMA (128 arrivals)
+  const uint32_t bar_kv_full = bars + 144;                 // [kStages]
+  const uint32_t bar_kv_empty = bars + 144 + 8 * kStages;  // [kStages]
+  const uint32_t tmem_slot = bars + 144 + 16 * kStages;    // u32 written by tcgen05.alloc
+  const uint32_t bar_clc_full = bars + 416;                // [2]  CLC response landed (16 tx bytes)
+  const uint32_t bar_clc_empty = bars + 432;               // [2]  all 14 consumer warps have read the response
+  const uint32_t clc_resp = bars + 448;                    // [2] x 16 B
+  const uint32_t s_inv_l = bars + 512;                     // [2 tiles][128 rows] fp32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- work assignment: one CTA = 256 query rows of one (b,h)
-  const int bh = blockIdx.x / a.num_q_blocks;
-  const int qi = blockIdx.x - bh * a.num_q_blocks;
-  const int qb = kCausal ? (a.num_q_blocks - 1 - qi) : qi;  // causal: longest blocks of a head first
-  const int q0 = qb * 2 * kBlockM;
-
-  // number of K/V tiles each Q tile visits (masked tiles above the diagonal are skipped)
-  const int n_kv_tiles = (a.Nkv + kBlockN - 1) / kBlockN;
-  auto tiles_for = [&](int r0) {
-    int n = (r0 < a.Nq) ? n_kv_tiles : 0;
-    if (kCausal && n > 0) {
-      const int last_row = min(r0 + kBlockM - 1, a.Nq - 1);
-      const int last_col = last_row + a.causal_off;   // largest visible key index
-      n = last_col < 0 ? 0 : min(n, last_col / kBlockN + 1);
-    }
-    return n;
+  constexpr uint32_t kClcConsumers = 14;   // producer lane + MMA warp + 8 softmax warps + 4 epilogue warps
+  // Every role walks the same item sequence: blockIdx.x first, then whatever the scheduler lane stole.
+  // The response for item t+1 is requested at the start of item t into slot (t+1)&1 and read by every
+  // consumer when it has finished item t.
+  auto next_item = [&](int t_next) -> int {
+    const uint32_t slot = uint32_t(t_next & 1);
+    mbar_wait(bar_clc_full + 8 * slot, uint32_t((t_next - 1) >> 1) & 1u, 500);   // use k = (t_next-1)/2 of the slot
+    const int id = clc_decode(clc_resp + 16 * slot);
+    return id;
   };
-  const int n_t0 = tiles_for(q0), n_t1 = tiles_for(q0 + kBlockM);
-  const int n_max = max(n_t0, n_t1);
+  auto release_item_slot = [&](int t_next) {   // one arrival per consumer warp, after all its lanes have read
+    mbar_arrive(bar_clc_empty + 8 * uint32_t(t_next & 1));
+  };
 
   // ---- one-time setup
-  if (warp == 8 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     prefetch_tensormap(&tmQ);
     prefetch_tensormap(&tmK);
     prefetch_tensormap(&tmV);
     prefetch_tensormap(&tmO);
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == 13 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_q_full + 8 * i, 1);
+      mbar_init(bar_q_empty + 8 * i, 1);
       mbar_init(bar_s_full + 8 * i, 1);
+      mbar_init(bar_o_full + 8 * i, 1);
+      mbar_init(bar_o_free + 8 * i, 128);
+      mbar_init(bar_ep_full + 8 * i, 128);
+      mbar_init(bar_ep_empty + 8 * i, 128);
       mbar_init(bar_p_full + 16 * i, 128);
       mbar_init(bar_p_full + 16 * i + 8, 128);
-      mbar_init(bar_o_full + 8 * i, 1);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_kv_full + 8 * s, 1);
       mbar_init(bar_kv_empty + 8 * s, 1);
     }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_clc_full + 8 * s, 1);
+      mbar_init(bar_clc_empty + 8 * s, kClcConsumers);
+    }
     fence_mbar_init();
   }
-  if (warp == 10) {
+  if (warp == 14) {
     tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
   }
@@ -194,34 +262,62 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp >= 8) {
-    setmaxnreg_dec<56>();
-    if (warp == 8) {
+  if (warp >= 12) {
+    setmaxnreg_dec<40>();
+    if (warp == 12) {
       // =========================== TMA producer ===========================
       if (lane == 0) {
-        auto load_tile = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int row0) {
-          mbar_arrive_expect_tx(bar, kTileBytes);
-#pragma unroll
-          for (int h = 0; h < kNumBoxes; ++h) tma_load_3d(dst + h * kBoxBytes, tm, bar, h * 64, row0, bh);
-        };
-        if (n_t0 > 0) load_tile(&tmQ, sQ, bar_q_full, q0);
-        int it = 0;
-        for (int j = 0; j < n_max; ++j) {
-#pragma unroll
-          for (int kv = 0; kv < 2; ++kv) {
-            const int stage = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            mbar_wait(bar_kv_empty + 8 * stage, ph ^ 1, 100 + kv);
-            load_tile(kv == 0 ? &tmK : &tmV, sKV + stage * kTileBytes, bar_kv_full + 8 * stage,
-                      j * kBlockN);
-            ++it;
-            if (j == 0 && kv == 0 && n_t1 > 0)
-              load_tile(&tmQ, sQ + kTileBytes, bar_q_full + 8, q0 + kBlockM);
+        int it = 0;                  // K/V ring position, runs across work items
+        uint32_t nq[2] = {0u, 0u};   // Q_i loads issued so far (a tile is skipped when it has no K/V tile to visit)
+        int w = blockIdx.x;
+        for (int t = 0; w >= 0; ++t) {
+          {  // scheduler: request the item after this one
+            const uint32_t slot = uint32_t((t + 1) & 1);
+            mbar_wait(bar_clc_empty + 8 * slot, (uint32_t(t >> 1) & 1u) ^ 1u, 120);   // use k = t/2 of the slot
+            mbar_arrive_expect_tx(bar_clc_full + 8 * slot, 16);
+            clc_try_cancel(clc_resp + 16 * slot, bar_clc_full + 8 * slot);
           }
+          const WorkItem wi = get_item<kCausal>(a, w);
+#ifdef FA_TRACE
+          if (a.trace != nullptr && blockIdx.x < 160 && t < 40) {   // which CTA ran which item, and when
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            a.trace[4096 + (blockIdx.x * 40 + t) * 2] = w + 1;
+            a.trace[4096 + (blockIdx.x * 40 + t) * 2 + 1] = (long long)now;
+          }
+#endif
+          auto load_tile = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int row0) {
+            mbar_arrive_expect_tx(bar, kTileBytes);
+#pragma unroll
+            for (int h = 0; h < kNumBoxes; ++h) tma_load_3d(dst + h * kBoxBytes, tm, bar, h * 64, row0, wi.bh);
+          };
+          // Q_i of the previous item must have been consumed by all of its QK^T MMAs
+          if (wi.n_t0 > 0) {
+            mbar_wait(bar_q_empty, (nq[0] & 1u) ^ 1u, 110);
+            load_tile(&tmQ, sQ, bar_q_full, wi.q0);
+            ++nq[0];
+          }
+          for (int j = 0; j < wi.n_max; ++j) {
+#pragma unroll
+            for (int kv = 0; kv < 2; ++kv) {
+              const int stage = it % kStages;
+              const uint32_t ph = (it / kStages) & 1;
+              mbar_wait(bar_kv_empty + 8 * stage, ph ^ 1, 100 + kv);
+              load_tile(kv == 0 ? &tmK : &tmV, sKV + stage * kTileBytes, bar_kv_full + 8 * stage, j * kBlockN);
+              ++it;
+              if (j == 0 && kv == 0 && wi.n_t1 > 0) {
+                mbar_wait(bar_q_empty + 8, (nq[1] & 1u) ^ 1u, 111);
+                load_tile(&tmQ, sQ + kTileBytes, bar_q_full + 8, wi.q0 + kBlockM);
+                ++nq[1];
+              }
+            }
+          }
+          w = next_item(t + 1);
+          release_item_slot(t + 1);
         }
       }
       __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == 13) {
       // =========================== MMA issuer ===========================
       // The whole warp runs the (uniform) control flow and the barrier waits; one elected lane issues
       // the tcgen05.mma / tcgen05.commit instructions.  Keeping the flow warp-uniform lets the compiler
@@ -230,10 +326,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t hi_qk = uint32_t(a.desc_hi_qk >> 32), hi_v = uint32_t(a.desc_hi_v >> 32);
       const uint32_t lo_qk = uint32_t(a.desc_hi_qk), lo_v = uint32_t(a.desc_hi_v);
       const uint32_t idesc_qk = a.idesc_qk, idesc_pv = a.idesc_pv;
-      int trace_j = 0;
-      (void)trace_j;
-      // S_i = Q_i K^T, then signal `bar_done` (and optionally release the K stage) when it has landed
-      auto issue_qk = [&](int i, int stage, uint32_t bar_done, uint32_t bar_release) {
+      // S_i = Q_i K^T; then signal `bar_done`, and up to two more barriers (K stage release, Q_i release)
+      auto issue_qk = [&](int i, int stage, uint32_t bar_done, uint32_t bar_rel_a, uint32_t bar_rel_b) {
         const uint32_t a_lo = lo_qk | ((sQ + i * kTileBytes) >> 4);
         const uint32_t b_lo = lo_qk | ((sKV + stage * kTileBytes) >> 4);
         const uint32_t d_tmem = tmem_base + i * kBlockN;
@@ -244,7 +338,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_ss(d_tmem, a_lo + off, hi_qk, b_lo + off, hi_qk, idesc_qk, k > 0 ? 1u : 0u);
           }
           umma_commit(bar_done);
-          if (bar_release) umma_commit(bar_release);
+          if (bar_rel_a) umma_commit(bar_rel_a);
+          if (bar_rel_b) umma_commit(bar_rel_b);
         }
         __syncwarp();
       };
@@ -258,7 +353,6 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int h = 0; h < 2; ++h) {
           mbar_wait(bar_p_full + 16 * i + 8 * h, parity, 212 + 2 * i + h);
           tc_fence_after();
-          if (lane == 0) FA_TRACE_EV(trace_j, 8 + 3 * i + h);
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 4 * h; k < 4 * h + 4; ++k)
@@ -274,214 +368,296 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto stage_of = [&](int it) { return it % kStages; };
       auto phase_of = [&](int it) { return uint32_t((it / kStages) & 1); };
 
-      if (n_max > 0) {
-        // S_i(0) = Q_i K_0^T
-        mbar_wait(bar_kv_full + 8 * stage_of(0), phase_of(0), 200);
-        const uint32_t rel = bar_kv_empty + 8 * stage_of(0);
-        if (n_t0 > 0) {
-          mbar_wait(bar_q_full, 0, 201);
-          tc_fence_after();
-          issue_qk(0, stage_of(0), bar_s_full, n_t1 > 0 ? 0u : rel);
+      int it0 = 0;                    // ring position of this item's K_0
+      uint32_t cnt[2] = {0u, 0u};     // S/P/O phase counters per tile (one per (tile, j) step, across items)
+      uint32_t nq[2] = {0u, 0u};      // Q_i tiles consumed so far
+      uint32_t ne[2] = {0u, 0u};      // epilogues of tile i started before this item (items where the tile is valid)
+      int w = blockIdx.x;
+      for (int t = 0; w >= 0; ++t) {
+        const WorkItem wi = get_item<kCausal>(a, w);
+        const int n_t0 = wi.n_t0, n_t1 = wi.n_t1, n_max = wi.n_max;
+        if (n_max > 0) {
+          // S_i(0) = Q_i K_0^T
+          mbar_wait(bar_kv_full + 8 * stage_of(it0), phase_of(it0), 200);
+          const uint32_t rel = bar_kv_empty + 8 * stage_of(it0);
+          if (n_t0 > 0) {
+            mbar_wait(bar_q_full, nq[0] & 1u, 201);
+            tc_fence_after();
+            issue_qk(0, stage_of(it0), bar_s_full, n_t1 > 0 ? 0u : rel, n_t0 == 1 ? bar_q_empty : 0u);
+          }
+          if (n_t1 > 0) {
+            mbar_wait(bar_q_full + 8, nq[1] & 1u, 202);
+            tc_fence_after();
+            issue_qk(1, stage_of(it0), bar_s_full + 8, rel, n_t1 == 1 ? bar_q_empty + 8 : 0u);
+          }
         }
-        if (n_t1 > 0) {
-          mbar_wait(bar_q_full + 8, 0, 202);
-          tc_fence_after();
-          issue_qk(1, stage_of(0), bar_s_full + 8, rel);
+        for (int j = 0; j < n_max; ++j) {
+          const int it_v = it0 + 2 * j + 1, it_k = it0 + 2 * j + 2;
+          const bool has_next = (j + 1 < n_max);
+          mbar_wait(bar_kv_full + 8 * stage_of(it_v), phase_of(it_v), 210);
+          if (has_next) mbar_wait(bar_kv_full + 8 * stage_of(it_k), phase_of(it_k), 211);
+          const uint32_t rel_v = bar_kv_empty + 8 * stage_of(it_v);
+          const uint32_t rel_k = bar_kv_empty + 8 * stage_of(it_k);
+          // n_t1 >= n_t0 whenever both tiles exist (the second tile sits lower in the causal triangle);
+          // tile 1 is absent (n_t1 == 0) only for a ragged last block.
+          if (j < n_t0) {
+            // the first PV of an item overwrites O_0: the epilogue must have read the previous item's O_0
+            if (j == 0) mbar_wait(bar_o_free, (ne[0] & 1u) ^ 1u, 220);
+            issue_pv(0, stage_of(it_v), j > 0, (cnt[0] + j) & 1u, bar_o_full, j < n_t1 ? 0u : rel_v);
+          }
+          if (j + 1 < n_t0)
+            issue_qk(0, stage_of(it_k), bar_s_full, j + 1 < n_t1 ? 0u : rel_k, j + 2 == n_t0 ? bar_q_empty : 0u);
+          if (j < n_t1) {
+            if (j == 0) mbar_wait(bar_o_free + 8, (ne[1] & 1u) ^ 1u, 221);
+            issue_pv(1, stage_of(it_v), j > 0, (cnt[1] + j) & 1u, bar_o_full + 8, rel_v);
+          }
+          if (j + 1 < n_t1)
+            issue_qk(1, stage_of(it_k), bar_s_full + 8, rel_k, j + 2 == n_t1 ? bar_q_empty + 8 : 0u);
         }
-      }
-      for (int j = 0; j < n_max; ++j) {
-        const int it_v = 2 * j + 1, it_k = 2 * j + 2;
-        const bool has_next = (j + 1 < n_max);
-        mbar_wait(bar_kv_full + 8 * stage_of(it_v), phase_of(it_v), 210);
-        if (has_next) mbar_wait(bar_kv_full + 8 * stage_of(it_k), phase_of(it_k), 211);
-        trace_j = j;
-        const uint32_t rel_v = bar_kv_empty + 8 * stage_of(it_v);
-        const uint32_t rel_k = bar_kv_empty + 8 * stage_of(it_k);
-        // n_t1 >= n_t0 whenever both tiles exist (the second tile sits lower in the causal triangle);
-        // tile 1 is absent (n_t1 == 0) only for a ragged last block.
-        if (j < n_t0) issue_pv(0, stage_of(it_v), j > 0, j & 1, bar_o_full, j < n_t1 ? 0u : rel_v);
-        if (j + 1 < n_t0) {
-          if (lane == 0) FA_TRACE_EV(j, 10);
-          issue_qk(0, stage_of(it_k), bar_s_full, j + 1 < n_t1 ? 0u : rel_k);
-        }
-        if (j < n_t1) issue_pv(1, stage_of(it_v), j > 0, j & 1, bar_o_full + 8, rel_v);
-        if (j + 1 < n_t1) {
-          if (lane == 0) FA_TRACE_EV(j, 13);
-          issue_qk(1, stage_of(it_k), bar_s_full + 8, rel_k);
-        }
+        it0 += 2 * n_max;
+        cnt[0] += uint32_t(n_t0);
+        cnt[1] += uint32_t(n_t1);
+        nq[0] += n_t0 > 0 ? 1u : 0u;
+        nq[1] += n_t1 > 0 ? 1u : 0u;
+        ne[0] += wi.valid0 ? 1u : 0u;
+        ne[1] += wi.valid1 ? 1u : 0u;
+        w = next_item(t + 1);
+        __syncwarp();
+        if (lane == 0) release_item_slot(t + 1);
       }
     }
+  } else if (warp >= 8) {
+    // =========================== correction / epilogue warpgroup ===========================
+    // Final correction of the accumulator: O_i * (1/l) -> 16-bit -> 128B-swizzled staging tile -> TMA store,
+    // running concurrently with the next work item.  1/l arrives from the softmax warpgroup through shared
+    // memory; O_i is released back to the MMA warp as soon as it is in registers.
+    setmaxnreg_dec<56>();
+    const int wl = warp & 3;
+    const int row_in_tile = wl * 32 + lane;
+    const uint32_t lane_addr = uint32_t(wl * 32) << 16;
+    uint32_t cnt[2] = {0u, 0u};
+    uint32_t ne[2] = {0u, 0u};      // hand-offs of tile i received so far
+    bool store_pending = false;
+    int w = blockIdx.x;
+    for (int t = 0; w >= 0; ++t) {
+      const WorkItem wi = get_item<kCausal>(a, w);
+      w = next_item(t + 1);     // read early: the slot is only recycled once every warp has let go of it
+      __syncwarp();
+      if (lane == 0) release_item_slot(t + 1);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (!(i ? wi.valid1 : wi.valid0)) continue;
+        const int n_i = i ? wi.n_t1 : wi.n_t0;
+        const uint32_t tO = tmem_base + lane_addr + 2 * kBlockN + i * D;
+        mbar_wait(bar_ep_full + 8 * i, ne[i] & 1u, 400 + i);
+        ++ne[i];
+        float inv_l;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(inv_l) : "r"(s_inv_l + uint32_t(i * 128 + row_in_tile) * 4u) : "memory");
+        mbar_arrive(bar_ep_empty + 8 * i);
+        if (n_i > 0) {
+          mbar_wait(bar_o_full + 8 * i, (cnt[i] + uint32_t(n_i) - 1u) & 1u, 410 + i);
+          tc_fence_after();
+        }
+        // staging tile free again?  (the previous TMA store must have finished reading it)
+        if (store_pending) {
+          if (row_in_tile == 0) tma_store_wait_read<0>();
+          named_bar_sync(2, 128);
+        }
+#pragma unroll
+        for (int q = 0; q < D / 32; ++q) {
+          uint32_t orow[32];
+          if (n_i > 0) {
+            tmem_ld32(tO + q * 32, orow);
+            tmem_wait_ld();
+            if (q == D / 32 - 1) {        // O_i is in registers: hand the accumulator back to the MMA warp
+              tc_fence_before();
+              mbar_arrive(bar_o_free + 8 * i);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) orow[k] = 0u;
+            if (q == D / 32 - 1) mbar_arrive(bar_o_free + 8 * i);
+          }
+          const uint32_t box = sO + (q / 2) * kBoxBytes + row_in_tile * 128;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint32_t wv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              wv[e] = pack2<kBF16>(__uint_as_float(orow[v * 8 + 2 * e]) * inv_l,
+                                   __uint_as_float(orow[v * 8 + 2 * e + 1]) * inv_l);
+            const uint32_t chunk = uint32_t((q & 1) * 4 + v);
+            const uint32_t addr = box + ((chunk ^ uint32_t(row_in_tile & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(wv[0]), "r"(wv[1]),
+                         "r"(wv[2]), "r"(wv[3]) : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (row_in_tile == 0) {
+#pragma unroll
+          for (int h = 0; h < kNumBoxes; ++h)
+            tma_store_3d(&tmO, sO + h * kBoxBytes, h * 64, wi.q0 + i * kBlockM, wi.bh);
+          tma_store_commit();
+        }
+        store_pending = true;
+        cnt[i] += uint32_t(n_i);
+      }
+    }
+    if (store_pending && row_in_tile == 0) tma_store_wait<0>();
   } else {
     // =========================== softmax warpgroups ===========================
-    setmaxnreg_inc<224>();
+    setmaxnreg_inc<208>();
     const int i = warp >> 2;           // which Q tile
     const int wl = warp & 3;           // warp within the warpgroup == TMEM lane quarter
     const int row_in_tile = wl * 32 + lane;
-    const int row = q0 + i * kBlockM + row_in_tile;
-    const int n_i = i ? n_t1 : n_t0;
     const uint32_t lane_addr = uint32_t(wl * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + i * kBlockN;
     const uint32_t tO = tmem_base + lane_addr + 2 * kBlockN + i * D;
     const uint32_t b_s_full = bar_s_full + 8 * i;
     const uint32_t b_p_full = bar_p_full + 16 * i;
     const uint32_t b_o_full = bar_o_full + 8 * i;
-
     const float c = a.scale_log2;
-    // last visible key index for this row
-    int limit = a.Nkv - 1;
-    if (kCausal) limit = min(limit, row + a.causal_off);
+    uint32_t cnt = 0;                  // S/P/O phase counter of this tile, across items
+    uint32_t ne = 0;                   // hand-offs to the epilogue warpgroup so far
+    int w = blockIdx.x;
+    for (int t = 0; w >= 0; ++t) {
+      const int w_cur = w;
+      int n_i, limit;
+      bool valid;
+      {
+        const WorkItem wi = get_item<kCausal>(a, w_cur);
+        valid = i ? wi.valid1 : wi.valid0;
+        n_i = i ? wi.n_t1 : wi.n_t0;
+        // last visible key index for this row
+        limit = a.Nkv - 1;
+        if (kCausal) limit = min(limit, wi.q0 + i * kBlockM + row_in_tile + a.causal_off);
+      }
+      w = next_item(t + 1);     // read early: the slot is only recycled once every warp has let go of it
+      __syncwarp();
+      if (lane == 0) release_item_slot(t + 1);
+      if (!valid) continue;
 
-    float m_ref = -INFINITY;   // max used in the exponents (lags the true max by <= threshold)
-    float m_true = -INFINITY;  // true running row max (scaled, log2 units)
-    float l = 0.f;             // sum of 2^(t - m_ref)
+      float m_ref = -INFINITY;   // max used in the exponents (lags the true max by <= threshold)
+      float m_true = -INFINITY;  // true running row max (scaled, log2 units)
+      float l = 0.f;             // sum of 2^(t - m_ref)
 
-    for (int j = 0; j < n_i; ++j) {
-      mbar_wait(b_s_full, j & 1, 300 + i);
-      tc_fence_after();
-      if (row_in_tile == 0) FA_TRACE_EV(j, 4 * i + 0);
-      uint32_t sr[4][32];
+      for (int j = 0; j < n_i; ++j) {
+        const uint32_t par = (cnt + uint32_t(j)) & 1u;
+        mbar_wait(b_s_full, par, 300 + i);
+        tc_fence_after();
+        if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 0);
+        uint32_t sr[4][32];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, sr[q]);
-      tmem_wait_ld();
-      if (row_in_tile == 0) FA_TRACE_EV(j, 4 * i + 1);
+        for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, sr[q]);
+        tmem_wait_ld();
+        if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 1);
 
-      // masking: key index > limit -> -inf (diagonal tiles of causal runs, ragged last tile)
-      const int lim_local = limit - j * kBlockN;
-      if (__any_sync(0xffffffffu, lim_local < kBlockN - 1)) {
+        // masking: key index > limit -> -inf (diagonal tiles of causal runs, ragged last tile)
+        const int lim_local = limit - j * kBlockN;
+        if (__any_sync(0xffffffffu, lim_local < kBlockN - 1)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (q * 32 + k > lim_local) sr[q][k] = 0xff800000u;  // -inf
+        }
+
+        // row max with four independent chains (a single chain of 64 dependent FMNMX3 costs ~4 clk each)
+        float mxp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (q * 32 + k > lim_local) sr[q][k] = 0xff800000u;  // -inf
-      }
+          for (int k = 0; k < 32; k += 8)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              mxp[u] = fmaxf(mxp[u], fmaxf(__uint_as_float(sr[q][k + 2 * u]), __uint_as_float(sr[q][k + 2 * u + 1])));
+        const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+        const float m_new = fmaxf(m_true, mx * c);
+        m_true = m_new;
 
-      // row max with four independent chains (a single chain of 64 dependent FMNMX3 costs ~4 clk each)
-      float mxp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int k = 0; k < 32; k += 8)
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            mxp[u] = fmaxf(mxp[u], fmaxf(__uint_as_float(sr[q][k + 2 * u]), __uint_as_float(sr[q][k + 2 * u + 1])));
-      const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
-      const float m_new = fmaxf(m_true, mx * c);
-      m_true = m_new;
-
-      if (j == 0) {
-        m_ref = m_new;
-      } else {
-        const bool moved = (m_new - m_ref) > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, moved)) {
-          // rescale this warp's 32 rows of O (and l) to the new reference max
-          const float alpha = (m_new == -INFINITY) ? 1.f : ex2_approx(m_ref - m_new);
+        if (j == 0) {
           m_ref = m_new;
-          l *= alpha;
-          mbar_wait(b_o_full, (j - 1) & 1, 310 + i);  // PV(j-1) has landed in TMEM
-          tc_fence_after();
+        } else {
+          const bool moved = (m_new - m_ref) > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, moved)) {
+            // rescale this warp's 32 rows of O (and l) to the new reference max
+            const float alpha = (m_new == -INFINITY) ? 1.f : ex2_approx(m_ref - m_new);
+            m_ref = m_new;
+            l *= alpha;
+            mbar_wait(b_o_full, par ^ 1u, 310 + i);  // PV(j-1) has landed in TMEM
+            tc_fence_after();
 #pragma unroll
-          for (int q = 0; q < D / 32; ++q) {
-            uint32_t orow[32];
-            tmem_ld32(tO + q * 32, orow);
-            tmem_wait_ld();
+            for (int q = 0; q < D / 32; ++q) {
+              uint32_t orow[32];
+              tmem_ld32(tO + q * 32, orow);
+              tmem_wait_ld();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) orow[k] = __float_as_uint(__uint_as_float(orow[k]) * alpha);
-            tmem_st32(tO + q * 32, orow);
+              for (int k = 0; k < 32; ++k) orow[k] = __float_as_uint(__uint_as_float(orow[k]) * alpha);
+              tmem_st32(tO + q * 32, orow);
+            }
           }
         }
-      }
-      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
 
-      // p = 2^(s*c - m_ref) with packed (2-wide) fp32 math; FA_EMU_PAIRS_OF_4 of every 4 pairs take the
-      // polynomial path, the rest MUFU.EX2.  P is published to the MMA warp in two halves of 64 keys.
-      const float2 c2 = make_float2(c, c), neg_m2 = make_float2(neg_m, neg_m);
-      float2 lsum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        // p = 2^(s*c - m_ref) with packed (2-wide) fp32 math; FA_EMU_PAIRS_OF_4 of every 4 pairs take the
+        // polynomial path, the rest MUFU.EX2.  P is published to the MMA warp in two halves of 64 keys.
+        const float2 c2 = make_float2(c, c), neg_m2 = make_float2(neg_m, neg_m);
+        float2 lsum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t pk[16];
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[q][2 * k]), __uint_as_float(sr[q][2 * k + 1])),
-                                      c2, neg_m2);
-          float2 pv;
-          if ((k & 3) < FA_EMU_PAIRS_OF_4) {
-            pv = ex2_emulated(x);
-          } else {
-            pv.x = ex2_approx(x.x);
-            pv.y = ex2_approx(x.y);
+          for (int k = 0; k < 16; ++k) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[q][2 * k]), __uint_as_float(sr[q][2 * k + 1])),
+                                        c2, neg_m2);
+            float2 pv;
+            if ((k & 3) < FA_EMU_PAIRS_OF_4) {
+              pv = ex2_emulated(x);
+            } else {
+              pv.x = ex2_approx(x.x);
+              pv.y = ex2_approx(x.y);
+            }
+            lsum2[k & 3] = __fadd2_rn(lsum2[k & 3], pv);
+            pk[k] = pack2<kBF16>(pv);
           }
-          lsum2[k & 3] = __fadd2_rn(lsum2[k & 3], pv);
-          pk[k] = pack2<kBF16>(pv);
+          tmem_st16(tS + q * 16, pk);   // P(16-bit) over the first 64 columns of S
+          if (q & 1) {
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(b_p_full + 8 * (q >> 1));
+            if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 2 + (q >> 1));
+          }
         }
-        tmem_st16(tS + q * 16, pk);   // P(16-bit) over the first 64 columns of S
-        if (q & 1) {
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(b_p_full + 8 * (q >> 1));
-          if (row_in_tile == 0) FA_TRACE_EV(j, 4 * i + 2 + (q >> 1));
-        }
+        const float2 lsum = __fadd2_rn(__fadd2_rn(lsum2[0], lsum2[1]), __fadd2_rn(lsum2[2], lsum2[3]));
+        l += lsum.x + lsum.y;
       }
-      const float2 lsum = __fadd2_rn(__fadd2_rn(lsum2[0], lsum2[1]), __fadd2_rn(lsum2[2], lsum2[3]));
-      l += lsum.x + lsum.y;
-    }
+      cnt += uint32_t(n_i);
 
-    // ---- epilogue: O_i / l -> 16-bit -> swizzled smem (dead Q tile) -> TMA store
-    if (q0 + i * kBlockM < a.Nq) {
-      if (n_i > 0) {
-        mbar_wait(b_o_full, (n_i - 1) & 1, 320 + i);
-        tc_fence_after();
-      }
+      // ---- hand the row normaliser to the epilogue warpgroup, write the row statistics, move on
       if (limit < 0) l = 0.f;   // row sees no key at all: the polynomial exp2 returns 2^-127, not 0
       const float inv_l = (l > 0.f) ? (1.f / l) : 0.f;
-      const uint32_t sO = sQ + i * kTileBytes;
-#pragma unroll
-      for (int q = 0; q < D / 32; ++q) {
-        uint32_t orow[32];
-        if (n_i > 0) {
-          tmem_ld32(tO + q * 32, orow);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) orow[k] = 0u;
-        }
-        const uint32_t box = sO + (q / 2) * kBoxBytes + row_in_tile * 128;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            w[e] = pack2<kBF16>(__uint_as_float(orow[v * 8 + 2 * e]) * inv_l,
-                                __uint_as_float(orow[v * 8 + 2 * e + 1]) * inv_l);
-          const uint32_t chunk = uint32_t((q & 1) * 4 + v);
-          const uint32_t addr = box + ((chunk ^ uint32_t(row_in_tile & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]),
-                       "r"(w[2]), "r"(w[3]) : "memory");
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + i, 128);
-      if (row_in_tile == 0) {
-#pragma unroll
-        for (int h = 0; h < kNumBoxes; ++h)
-          tma_store_3d(&tmO, sO + h * kBoxBytes, h * 64, q0 + i * kBlockM, bh);
-        tma_store_commit();
-      }
+      mbar_wait(bar_ep_empty + 8 * i, (ne & 1u) ^ 1u, 330 + i);   // slot of the previous hand-off consumed
+      ++ne;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_inv_l + uint32_t(i * 128 + row_in_tile) * 4u), "f"(inv_l) : "memory");
+      mbar_arrive(bar_ep_full + 8 * i);
+      const WorkItem wi = get_item<kCausal>(a, w_cur);   // recomputed here to keep it out of the hot loop's registers
+      const int row = wi.q0 + i * kBlockM + row_in_tile;
       if (row < a.Nq) {
-        const long long off = (long long)bh * a.stat_stride_bh + row;
+        const long long off = (long long)wi.bh * a.stat_stride_bh + row;
         const float ln2 = 0.6931471805599453f;
         const bool any = l > 0.f;
         if (a.lse) a.lse[off] = any ? fmaf(m_ref, ln2, logf(l)) : -INFINITY;
         if (a.m) a.m[off] = any ? m_true * ln2 : -INFINITY;
         if (a.l) a.l[off] = any ? l * ex2_approx(m_ref - m_true) : 0.f;
       }
-      if (row_in_tile == 0) tma_store_wait_read<0>();
     }
   }
 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) {
+  if (warp == 14) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }

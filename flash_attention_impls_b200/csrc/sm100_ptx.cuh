@@ -72,6 +72,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
+// ---------------------------------------------------------------- cluster launch control (CLC)
+// Blackwell's hardware work-stealing for persistent kernels: a running CTA asks the launch hardware to
+// cancel a CTA of the same grid that has not started yet and takes over its blockIdx.  The 16-byte
+// response lands in shared memory through the async proxy and completes 16 tx bytes on an mbarrier.
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_smem, uint32_t bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+      ::"r"(resp_smem), "r"(bar) : "memory");
+}
+// Decodes a response: the stolen blockIdx.x, or -1 when there was nothing left to steal.
+__device__ __forceinline__ int clc_decode(uint32_t resp_smem) {
+  uint32_t ok, x;
+  asm volatile(
+      "{\n\t.reg .b128 r;\n\t.reg .pred p;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "mov.u32 %1, 0;\n\t"
+      "@p clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %1, r;\n\t}\n"
+      : "=r"(ok), "=r"(x) : "r"(resp_smem) : "memory");
+  return ok ? int(x) : -1;
+}
+
 // ---------------------------------------------------------------- named barriers / regs
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
