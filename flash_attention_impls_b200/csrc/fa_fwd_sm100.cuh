@@ -122,8 +122,12 @@ __device__ __forceinline__ float2 ex2_emulated(float2 x) {
   return p;
 }
 
+// Of every 4 score pairs, this many take the polynomial path instead of MUFU.EX2.  Measured on the final
+// (persistent, 208-register softmax) kernel: 0 -> c4 1276 / causal-16k 1332 TFLOP/s, 1 -> 1250 / 1307,
+// 2 -> 1184 / 1237 (profiles/r01_sweep_v7_exp2_fraction.log): the extra FMA-pipe instructions and registers
+// cost more than the MUFU cycles they free, so the default is 0; the switch stays for d = 64 experiments.
 #ifndef FA_EMU_PAIRS_OF_4
-#define FA_EMU_PAIRS_OF_4 1   // of every 4 score pairs, this many take the polynomial path
+#define FA_EMU_PAIRS_OF_4 0
 #endif
 
 // One work item = 256 query rows of one (b,h).  Every role walks the same deterministic item list.
