@@ -23,7 +23,7 @@ STATUS = {
 # every symbol include/fa_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
     "fa_b200_forward", "fa_b200_forward_legacy", "fa_b200_forward_fp16", "fa_b200_merge_partial",
-    "fa_b200_cast_output", "fa_b200_launch_count", "fa_b200_last_error", "fa_b200_status_string",
+    "fa_b200_cast_output", "fa_b200_work_item", "fa_b200_launch_count", "fa_b200_last_error", "fa_b200_status_string",
     "fa_b200_version",
 )
 
@@ -73,6 +73,8 @@ def load() -> ctypes.CDLL:
     lib.fa_b200_merge_partial.restype = c_int
     lib.fa_b200_cast_output.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.fa_b200_cast_output.restype = c_int
+    lib.fa_b200_work_item.argtypes = [c_int] * 7 + [POINTER(c_int)] * 4
+    lib.fa_b200_work_item.restype = c_int
     lib.fa_b200_launch_count.argtypes = []
     lib.fa_b200_launch_count.restype = c_uint64
     lib.fa_b200_last_error.argtypes = []
@@ -88,6 +90,15 @@ def load() -> ctypes.CDLL:
 def check(status: int) -> None:
     if status != 0:
         raise FaB200Error(status, load().fa_b200_last_error().decode())
+
+
+def work_item(B: int, H: int, N: int, d: int, causal: bool, index: int, N_kv: int = 0):
+    """(num_items, bh, q0, tiles0, tiles1) of work item `index` of the launch for this shape (host-only)."""
+    out = [c_int(0) for _ in range(4)]
+    n = load().fa_b200_work_item(B, H, N, N_kv, d, 1 if causal else 0, index, *[ctypes.byref(x) for x in out])
+    if n == 0:
+        raise FaB200Error(2, load().fa_b200_last_error().decode())
+    return (n,) + tuple(x.value for x in out)
 
 
 def launch_count() -> int:

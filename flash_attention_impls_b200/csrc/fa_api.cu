@@ -149,9 +149,47 @@ unsigned long long env_u64(const char* name, unsigned long long dflt) {
   return s ? strtoull(s, nullptr, 0) : dflt;
 }
 
+// Shape / scheduling part of the kernel arguments (shared by the launch path and fa_b200_work_item).
+void fill_schedule(fa::FwdArgs& a, long long BH, int Nq, int Nkv, int d) {
+  const long long num_q_blocks = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
+  a.Nq = Nq;
+  a.Nkv = Nkv;
+  a.causal_off = Nkv - Nq;
+  a.num_q_blocks = (int)num_q_blocks;
+  a.num_items = (int)(BH * num_q_blocks);
+  a.num_bh = (int)BH;
+  // heads whose K and V (2 * N_kv * d * 2 bytes each) fit in about half of the 126 MB L2 together
+  const long long kv_bytes_per_head = 4LL * Nkv * d;
+  long long g = (64LL << 20) / (kv_bytes_per_head > 0 ? kv_bytes_per_head : 1);
+  g = std::max<long long>(1, std::min<long long>(g, BH));
+  a.group_heads = (int)env_u64("FA_B200_GROUP_HEADS", (unsigned long long)g);
+  if (a.group_heads < 1) a.group_heads = 1;
+  if (a.group_heads > BH) a.group_heads = (int)BH;
+}
+
 }  // namespace
 
 extern "C" {
+
+int fa_b200_work_item(int B, int H, int N, int N_kv, int d, int causal, int index, int* bh, int* q0,
+                      int* tiles0, int* tiles1) {
+  if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || (d != 64 && d != 128)) {
+    fail(FA_B200_ERR_SHAPE, "work_item: bad shape");
+    return 0;
+  }
+  fa::FwdArgs a{};
+  fill_schedule(a, (long long)B * H, N, N_kv ? N_kv : N, d);
+  if (index < 0 || index >= a.num_items) {
+    fail(FA_B200_ERR_SHAPE, "work_item: index %d outside [0, %d)", index, a.num_items);
+    return 0;
+  }
+  const fa::WorkItem wi = causal ? fa::get_item<true>(a, index) : fa::get_item<false>(a, index);
+  if (bh) *bh = wi.bh;
+  if (q0) *q0 = wi.q0;
+  if (tiles0) *tiles0 = wi.n_t0;
+  if (tiles1) *tiles1 = wi.n_t1;
+  return a.num_items;
+}
 
 int fa_b200_forward(const fa_b200_params* p) {
   if (!p) return fail(FA_B200_ERR_NULL, "params is NULL");
@@ -192,21 +230,7 @@ int fa_b200_forward(const fa_b200_params* p) {
   a.lse = p->lse;
   a.l = p->l;
   a.m = p->m;
-  a.Nq = Nq;
-  a.Nkv = Nkv;
-  a.causal_off = Nkv - Nq;
-  a.num_q_blocks = (int)num_q_blocks;
-  a.num_items = (int)(BH * num_q_blocks);
-  a.num_bh = (int)BH;
-  {
-    // heads whose K and V (2 * N_kv * d * 2 bytes each) fit in about half of the 126 MB L2 together
-    const long long kv_bytes_per_head = 4LL * Nkv * d;
-    long long g = (64LL << 20) / (kv_bytes_per_head > 0 ? kv_bytes_per_head : 1);
-    g = std::max<long long>(1, std::min<long long>(g, BH));
-    a.group_heads = (int)env_u64("FA_B200_GROUP_HEADS", (unsigned long long)g);
-    if (a.group_heads < 1) a.group_heads = 1;
-    if (a.group_heads > BH) a.group_heads = (int)BH;
-  }
+  fill_schedule(a, BH, Nq, Nkv, d);
   a.scale_log2 = scale * 1.4426950408889634f;
   a.stat_stride_bh = ss;
   const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;

@@ -137,7 +137,7 @@ struct WorkItem {
 };
 
 template <bool kCausal>
-__device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
+__host__ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
   WorkItem it;
   int qb;
   if (kCausal) {
@@ -148,7 +148,7 @@ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
     const int per_group = a.group_heads * a.num_q_blocks;
     const int g = w / per_group;
     const int r = w - g * per_group;
-    const int heads = min(a.group_heads, a.num_bh - g * a.group_heads);
+    const int heads = (a.group_heads < a.num_bh - g * a.group_heads) ? a.group_heads : (a.num_bh - g * a.group_heads);
     const int qi = r / heads;
     it.bh = g * a.group_heads + (r - qi * heads);
     qb = a.num_q_blocks - 1 - qi;
@@ -162,15 +162,16 @@ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
   auto tiles_for = [&](int r0) {
     int n = (r0 < a.Nq) ? n_kv_tiles : 0;
     if (kCausal && n > 0) {
-      const int last_row = min(r0 + kBlockM - 1, a.Nq - 1);
+      const int last_row = (r0 + kBlockM - 1 < a.Nq - 1) ? (r0 + kBlockM - 1) : (a.Nq - 1);
       const int last_col = last_row + a.causal_off;   // largest visible key index
-      n = last_col < 0 ? 0 : min(n, last_col / kBlockN + 1);
+      const int n_vis = last_col / kBlockN + 1;
+      n = last_col < 0 ? 0 : (n < n_vis ? n : n_vis);
     }
     return n;
   };
   it.n_t0 = tiles_for(it.q0);
   it.n_t1 = tiles_for(it.q0 + kBlockM);
-  it.n_max = max(it.n_t0, it.n_t1);
+  it.n_max = it.n_t0 > it.n_t1 ? it.n_t0 : it.n_t1;
   it.valid0 = it.q0 < a.Nq;
   it.valid1 = it.q0 + kBlockM < a.Nq;
   return it;

@@ -105,6 +105,14 @@ int fa_b200_merge_partial(float* O_acc, float* lse_acc, const void* O_part, cons
 /* Final cast of the fp32 ring accumulator to dtype: O[rows,d] = (dtype) O_acc[rows,d]. */
 int fa_b200_cast_output(void* O, const float* O_acc, int64_t rows, int d, int dtype, void* stream);
 
+/* Introspection of the tile scheduler (host-only, no GPU needed): decodes work item `index` of the launch that
+ * fa_b200_forward would make for this shape - which (b*H+h) slice, first query row, and how many 128-key K/V
+ * tiles each of its two 128-row Q tiles visits (0 = tile skipped).  Returns the number of work items
+ * (= grid size); on error returns 0 and sets fa_b200_last_error().  The item list is head-major; causal launches order items longest-first inside groups
+ * of heads whose K/V fit the L2 together. */
+int fa_b200_work_item(int B, int H, int N, int N_kv, int d, int causal, int index, int* bh, int* q0,
+                      int* tiles0, int* tiles1);
+
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t fa_b200_launch_count(void);
 

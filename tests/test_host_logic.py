@@ -37,3 +37,58 @@ def test_zigzag_round_trip_and_balance(P):
 def test_zigzag_requires_divisibility():
     with pytest.raises(ValueError):
         zigzag_split(torch.zeros(1, 1, 10, 4), 4, 0)
+
+
+# ----------------------------------------------------------------------------- tile scheduler order
+@pytest.mark.parametrize("B,H,N,Nkv,d,causal,group", [
+    (4, 32, 8192, 0, 128, False, None), (4, 32, 8192, 0, 128, True, None), (2, 24, 1100, 0, 128, True, "5"),
+    (1, 7, 520, 0, 64, True, "3"), (3, 5, 300, 900, 64, True, None), (1, 9, 900, 300, 128, True, "4"),
+    (1, 1, 1, 0, 64, True, None),
+])
+def test_work_item_list_is_a_permutation_with_the_right_trip_counts(monkeypatch, B, H, N, Nkv, d, causal, group):
+    """fa_b200_work_item decodes the kernel's own item mapping (get_item): every (b*H+h, q-block) exactly once,
+    trip counts that skip the K/V tiles above the causal diagonal, and - for causal launches - items ordered
+    longest-first inside each group of heads."""
+    from flash_attention_impls_b200 import _lib
+    if group is not None:
+        monkeypatch.setenv("FA_B200_GROUP_HEADS", group)
+    else:
+        monkeypatch.delenv("FA_B200_GROUP_HEADS", raising=False)
+    nkv = Nkv or N
+    n_items = _lib.work_item(B, H, N, d, causal, 0, Nkv)[0]
+    nqb = (N + 255) // 256
+    assert n_items == B * H * nqb
+    seen, per_group_cost = set(), {}
+    items = [_lib.work_item(B, H, N, d, causal, i, Nkv)[1:] for i in range(n_items)]
+    for idx, (bh, q0, t0, t1) in enumerate(items):
+        assert 0 <= bh < B * H and q0 % 256 == 0 and 0 <= q0 < nqb * 256
+        assert (bh, q0) not in seen
+        seen.add((bh, q0))
+        for tile, t in ((0, t0), (1, t1)):
+            r0 = q0 + 128 * tile
+            if r0 >= N:
+                want = 0
+            elif not causal:
+                want = (nkv + 127) // 128
+            else:
+                last_col = min(r0 + 127, N - 1) + (nkv - N)
+                want = 0 if last_col < 0 else min((nkv + 127) // 128, last_col // 128 + 1)
+            assert t == want
+    assert len(seen) == n_items
+    if causal:
+        # inside a group the q-blocks are visited in descending order (heaviest first)
+        g = int(group) if group else max(1, min(B * H, (64 << 20) // (4 * nkv * d)))
+        per = g * nqb
+        for start in range(0, n_items, per):
+            q0s = [q0 for (_, q0, _, _) in items[start:start + per]]
+            assert q0s == sorted(q0s, reverse=True)
+            heads = {bh for (bh, _, _, _) in items[start:start + per]}
+            assert len(heads) <= g and max(heads) - min(heads) < g
+
+
+def test_work_item_rejects_bad_arguments():
+    from flash_attention_impls_b200 import _lib
+    with pytest.raises(_lib.FaB200Error):
+        _lib.work_item(1, 1, 128, 64, False, 5)
+    with pytest.raises(_lib.FaB200Error):
+        _lib.work_item(1, 1, 128, 32, False, 0)
