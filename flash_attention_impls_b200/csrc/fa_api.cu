@@ -62,11 +62,11 @@ int make_tmap(CUtensorMap* tm, const void* base, int dtype, int d, int rows, lon
   if (!enc) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, (cuuint64_t)bh};
   cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)stride_bh_elems * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {(cuuint32_t)(d >= 64 ? 64 : 32), 128, 1};   // d = 32: one 64-byte-row box, 64B swizzle
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, dtype == FA_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                    3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   d >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return FA_B200_OK;
@@ -173,7 +173,7 @@ extern "C" {
 
 int fa_b200_work_item(int B, int H, int N, int N_kv, int d, int causal, int index, int* bh, int* q0,
                       int* tiles0, int* tiles1) {
-  if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || (d != 64 && d != 128)) {
+  if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || (d != 32 && d != 64 && d != 128)) {
     fail(FA_B200_ERR_SHAPE, "work_item: bad shape");
     return 0;
   }
@@ -196,8 +196,8 @@ int fa_b200_forward(const fa_b200_params* p) {
   if (!p->Q || !p->K || !p->V || !p->O) return fail(FA_B200_ERR_NULL, "Q, K, V and O must be non-NULL");
   if (p->B <= 0 || p->H <= 0 || p->N <= 0 || p->N_kv < 0)
     return fail(FA_B200_ERR_SHAPE, "bad shape B=%d H=%d N=%d N_kv=%d", p->B, p->H, p->N, p->N_kv);
-  if (p->d != 64 && p->d != 128)
-    return fail(FA_B200_ERR_HEAD_DIM, "unsupported head_dim=%d (supported: 64, 128)", p->d);
+  if (p->d != 32 && p->d != 64 && p->d != 128)
+    return fail(FA_B200_ERR_HEAD_DIM, "unsupported head_dim=%d (supported: 32, 64, 128)", p->d);
   if (p->dtype != FA_B200_FP16 && p->dtype != FA_B200_BF16)
     return fail(FA_B200_ERR_DTYPE, "unsupported dtype=%d (0 = fp16, 1 = bf16)", p->dtype);
   const long long BH = (long long)p->B * p->H;
@@ -234,11 +234,17 @@ int fa_b200_forward(const fa_b200_params* p) {
   a.scale_log2 = scale * 1.4426950408889634f;
   a.stat_stride_bh = ss;
   const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;
-  // Q, K: K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.
-  a.desc_hi_qk = fa::umma_desc_hi_bits(16, 1024, 2);
-  // V: MN-major (d contiguous), 128B swizzle: 64-column halves one box (16 KB) apart (LBO),
-  // 8-key groups 1024 B apart (SBO).
-  a.desc_hi_v = fa::umma_desc_hi_bits(fa::FwdTraits<128>::kBoxBytes, 1024, 2);
+  if (d >= 64) {
+    // Q, K: K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.
+    a.desc_hi_qk = fa::umma_desc_hi_bits(16, 1024, 2);
+    // V: MN-major (d contiguous), 128B swizzle: 64-column halves one box (16 KB) apart (LBO),
+    // 8-key groups 1024 B apart (SBO).
+    a.desc_hi_v = fa::umma_desc_hi_bits(fa::FwdTraits<128>::kBoxBytes, 1024, 2);
+  } else {
+    // d = 32: 64-byte rows, 64B swizzle (layout type 4): 8-row groups 512 B apart
+    a.desc_hi_qk = fa::umma_desc_hi_bits(16, 512, 4);
+    a.desc_hi_v = fa::umma_desc_hi_bits(fa::FwdTraits<32>::kBoxBytes, 512, 4);
+  }
   a.idesc_qk = fa::umma_idesc(fmt, 0, 0, 128, 128);
   a.idesc_pv = fa::umma_idesc(fmt, 0, 1, 128, (unsigned)d);
   // bring-up overrides (debug only)
@@ -257,6 +263,9 @@ int fa_b200_forward(const fa_b200_params* p) {
   if (d == 128) {
     if (bf16) { if (causal) FA_LAUNCH(128, true, true); else FA_LAUNCH(128, true, false); }
     else      { if (causal) FA_LAUNCH(128, false, true); else FA_LAUNCH(128, false, false); }
+  } else if (d == 32) {
+    if (bf16) { if (causal) FA_LAUNCH(32, true, true); else FA_LAUNCH(32, true, false); }
+    else      { if (causal) FA_LAUNCH(32, false, true); else FA_LAUNCH(32, false, false); }
   } else {
     if (bf16) { if (causal) FA_LAUNCH(64, true, true); else FA_LAUNCH(64, true, false); }
     else      { if (causal) FA_LAUNCH(64, false, true); else FA_LAUNCH(64, false, false); }

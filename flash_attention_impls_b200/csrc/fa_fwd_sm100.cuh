@@ -70,14 +70,18 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 template <int D>
 struct FwdTraits {
   static constexpr int kTileBytes = kBlockN * D * 2;       // one Q/K/V/O tile, 16-bit elements
-  static constexpr int kBoxBytes = 128 * 64 * 2;           // one 64-column TMA box (128B swizzle)
-  static constexpr int kNumBoxes = D / 64;
+  // A tile is stored as TMA boxes of 128 rows x kBoxCols columns: 64 columns (128-byte rows, 128B swizzle) for
+  // d >= 64, one 32-column box (64-byte rows, 64B swizzle) for d = 32.
+  static constexpr int kBoxCols = D >= 64 ? 64 : 32;
+  static constexpr int kRowBytes = kBoxCols * 2;
+  static constexpr int kBoxBytes = 128 * kRowBytes;
+  static constexpr int kNumBoxes = D / kBoxCols;
   static constexpr int kAuxBytes = 3072;                   // mbarriers (512 B) + 1/l hand-off (1 KB) + slack
   // shared memory: Q0 | Q1 | O staging (one tile) | K/V ring | aux
   static constexpr int kStagesMax = (kSmemLimit - kAuxBytes - 3 * kTileBytes) / kTileBytes;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
   static constexpr int kSmemBytes = (3 + kStages) * kTileBytes + kAuxBytes;
-  static_assert(D == 64 || D == 128, "head_dim must be 64 or 128");
+  static_assert(D == 32 || D == 64 || D == 128, "head_dim must be 32, 64 or 128");
   static_assert(kStages >= 3, "K/V ring too shallow");
 };
 
@@ -187,6 +191,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t kTileBytes = T::kTileBytes;
   constexpr uint32_t kBoxBytes = T::kBoxBytes;
   constexpr int kNumBoxes = T::kNumBoxes;
+  constexpr int kBoxCols = T::kBoxCols;
+  constexpr uint32_t kRowBytes = T::kRowBytes;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -294,7 +300,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           auto load_tile = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int row0) {
             mbar_arrive_expect_tx(bar, kTileBytes);
 #pragma unroll
-            for (int h = 0; h < kNumBoxes; ++h) tma_load_3d(dst + h * kBoxBytes, tm, bar, h * 64, row0, wi.bh);
+            for (int h = 0; h < kNumBoxes; ++h) tma_load_3d(dst + h * kBoxBytes, tm, bar, h * kBoxCols, row0, wi.bh);
           };
           // Q_i of the previous item must have been consumed by all of its QK^T MMAs
           if (wi.n_t0 > 0) {
@@ -361,7 +367,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 4 * h; k < 4 * h + 4; ++k)
-              umma_ts(d_tmem, p_tmem + k * 8, b_lo + k * (16 * 128 / 16), hi_v, idesc_pv, (acc || k > 0) ? 1u : 0u);
+              umma_ts(d_tmem, p_tmem + k * 8, b_lo + k * (16 * kRowBytes / 16), hi_v, idesc_pv, (acc || k > 0) ? 1u : 0u);
             if (h == 1) {
               umma_commit(bar_done);
               if (bar_release) umma_commit(bar_release);
@@ -483,7 +489,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int k = 0; k < 32; ++k) orow[k] = 0u;
             if (q == D / 32 - 1) mbar_arrive(bar_o_free + 8 * i);
           }
-          const uint32_t box = sO + (q / 2) * kBoxBytes + row_in_tile * 128;
+          // 16-byte chunk (q*4 + v) of this row: box (chunk / chunks-per-row), swizzled inside the box row
+          constexpr uint32_t kChunksPerRow = kRowBytes / 16;                 // 8 (128B swizzle) or 4 (64B swizzle)
+          const uint32_t swz = (kRowBytes == 128) ? uint32_t(row_in_tile & 7) : uint32_t((row_in_tile >> 1) & 3);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             uint32_t wv[4];
@@ -491,8 +499,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int e = 0; e < 4; ++e)
               wv[e] = pack2<kBF16>(__uint_as_float(orow[v * 8 + 2 * e]) * inv_l,
                                    __uint_as_float(orow[v * 8 + 2 * e + 1]) * inv_l);
-            const uint32_t chunk = uint32_t((q & 1) * 4 + v);
-            const uint32_t addr = box + ((chunk ^ uint32_t(row_in_tile & 7)) << 4);
+            const uint32_t c16 = uint32_t(q * 4 + v);
+            const uint32_t addr = sO + (c16 / kChunksPerRow) * kBoxBytes + row_in_tile * kRowBytes +
+                                  (((c16 % kChunksPerRow) ^ swz) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(wv[0]), "r"(wv[1]),
                          "r"(wv[2]), "r"(wv[3]) : "memory");
           }
@@ -502,7 +511,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (row_in_tile == 0) {
 #pragma unroll
           for (int h = 0; h < kNumBoxes; ++h)
-            tma_store_3d(&tmO, sO + h * kBoxBytes, h * 64, wi.q0 + i * kBlockM, wi.bh);
+            tma_store_3d(&tmO, sO + h * kBoxBytes, h * kBoxCols, wi.q0 + i * kBlockM, wi.bh);
           tma_store_commit();
         }
         store_pending = true;

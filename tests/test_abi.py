@@ -65,7 +65,7 @@ def _params(**kw):
 
 @pytest.mark.parametrize("kw,status", [
     (dict(Q=None), 1), (dict(O=None), 1), (dict(B=0), 2), (dict(N=-5), 2), (dict(N_kv=-1), 2),
-    (dict(d=32), 3), (dict(d=96), 3), (dict(d=256), 3), (dict(dtype=7), 4),
+    (dict(d=48), 3), (dict(d=96), 3), (dict(d=256), 3), (dict(dtype=7), 4),
     (dict(Q=0x1008), 5), (dict(q_stride_bh=8 * 1024 + 4), 5), (dict(q_stride_bh=64), 2),
 ])
 def test_argument_validation_returns_codes_without_a_gpu(kw, status):

@@ -71,6 +71,11 @@ SHAPES = [
     (1, 2, 300, 900, 64, "bf16", True),       # causal, bottom-right aligned
     (1, 2, 900, 300, 128, "fp16", True),      # N_kv < N: the first 600 rows see no key -> O = 0, lse = -inf
     (1, 1, 512, 130, 128, "bf16", False),
+    # head_dim 32 (64-byte-swizzle boxes): the reference's dispatchers accept it (flash_attn_cutlass.cu:531) and it is
+    # the Triton script's own correctness shape B=1 H=16 N=1024 D=32 causal (FA2-triton.py:332-344)
+    (1, 16, 1024, 1024, 32, "fp16", True),
+    (2, 3, 333, 333, 32, "bf16", False),
+    (1, 2, 128, 700, 32, "fp16", True),
     # more work items than SMs: resident CTAs steal items through cluster launch control
     (2, 200, 520, 520, 128, "bf16", True),    # 1200 items, ragged last q-block whose second tile is absent
     (3, 50, 300, 300, 64, "bf16", False),     # 300 items, second tile absent in every other item
@@ -206,7 +211,7 @@ def test_reference_surface_entry_points(fa):
 
 def test_unsupported_head_dim_is_an_error_not_a_silent_skip(fa):
     dev = torch.device("cuda:0")
-    x = torch.zeros(1, 1, 128, 32, dtype=torch.float16, device=dev)
+    x = torch.zeros(1, 1, 128, 96, dtype=torch.float16, device=dev)
     with pytest.raises(fa.FaB200Error) as e:
         fa.attention_forward(x, x, x)
     assert e.value.status == 3

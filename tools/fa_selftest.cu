@@ -279,7 +279,8 @@ umma_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using namespace fa;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t kTile = 128 * D * 2, kBox = 128 * 64 * 2;
+  constexpr int kBoxCols = D >= 64 ? 64 : 32;
+  constexpr uint32_t kTile = 128 * D * 2, kBox = 128 * kBoxCols * 2;
   const uint32_t sA = base, sB = base + kTile, sV = base + 2 * kTile, bars = base + 3 * kTile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -292,10 +293,10 @@ umma_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(bars + 32));
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bars, 3 * kTile);
-    for (int h = 0; h < D / 64; ++h) {
-      tma_load_3d(sA + h * kBox, &tmA, bars, h * 64, 0, 0);
-      tma_load_3d(sB + h * kBox, &tmB, bars, h * 64, 0, 0);
-      tma_load_3d(sV + h * kBox, &tmV, bars, h * 64, 0, 0);
+    for (int h = 0; h < D / kBoxCols; ++h) {
+      tma_load_3d(sA + h * kBox, &tmA, bars, h * kBoxCols, 0, 0);
+      tma_load_3d(sB + h * kBox, &tmB, bars, h * kBoxCols, 0, 0);
+      tma_load_3d(sV + h * kBox, &tmV, bars, h * kBoxCols, 0, 0);
     }
     mbar_wait(bars, 0, 1);
     tc_fence_after();
@@ -357,20 +358,21 @@ static int make_tmap_2d(CUtensorMap* tm, void* base, int d, int rows) {
                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, 1};
   cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)rows * d * 2};
-  cuuint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+  cuuint32_t box[3] = {(cuuint32_t)(d >= 64 ? 64 : 32), 128, 1}, es[3] = {1, 1, 1};
   CUresult r = ((Enc)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         d >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;
 }
 
 template <int D>
 static int run_umma_d(int argc, char** argv) {
   UnitArgs a;
-  const unsigned lbo_v = argc > 3 ? atoi(argv[3]) : 16384, sbo_v = argc > 4 ? atoi(argv[4]) : 1024;
-  a.kstep_v_bytes = argc > 5 ? atoi(argv[5]) : 2048;
-  const unsigned lbo_qk = argc > 6 ? atoi(argv[6]) : 16, sbo_qk = argc > 7 ? atoi(argv[7]) : 1024;
-  a.desc_hi_qk = fa::umma_desc_hi_bits(lbo_qk, sbo_qk, 2);
-  a.desc_hi_v = fa::umma_desc_hi_bits(lbo_v, sbo_v, 2);
+  const unsigned row_bytes = D >= 64 ? 128 : 64, layout = D >= 64 ? 2 : 4;   // 128B / 64B swizzle
+  const unsigned lbo_v = argc > 3 ? atoi(argv[3]) : 128 * row_bytes, sbo_v = argc > 4 ? atoi(argv[4]) : 8 * row_bytes;
+  a.kstep_v_bytes = argc > 5 ? atoi(argv[5]) : 16 * row_bytes;
+  const unsigned lbo_qk = argc > 6 ? atoi(argv[6]) : 16, sbo_qk = argc > 7 ? atoi(argv[7]) : 8 * row_bytes;
+  a.desc_hi_qk = fa::umma_desc_hi_bits(lbo_qk, sbo_qk, layout);
+  a.desc_hi_v = fa::umma_desc_hi_bits(lbo_v, sbo_v, layout);
   a.idesc_qk = fa::umma_idesc(1, 0, 0, 128, 128);
   a.idesc_pv = fa::umma_idesc(1, 0, 1, 128, D);
   const size_t n = 128 * D;
@@ -428,7 +430,7 @@ int main(int argc, char** argv) {
   if (mode == "ref") return run_ref(argc, argv);
   if (mode == "umma") {
     const int D = argc > 2 ? atoi(argv[2]) : 128;
-    return D == 64 ? run_umma_d<64>(argc, argv) : run_umma_d<128>(argc, argv);
+    return D == 32 ? run_umma_d<32>(argc, argv) : D == 64 ? run_umma_d<64>(argc, argv) : run_umma_d<128>(argc, argv);
   }
   return 2;
 }
