@@ -589,6 +589,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
         const float m_new = fmaxf(m_true, mx * c);
         m_true = m_new;
+        if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 14 + i);
 
         if (j == 0) {
           m_ref = m_new;
