@@ -178,73 +178,64 @@ def cast_output(o_acc: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 class HostPipeline:
     """End-to-end path for HOST buffers: pinned host Q,K,V -> device -> kernel -> pinned host O, lse.
 
-    The (b,h) slices are independent, so the call is pipelined over `chunks` groups of slices on three
-    streams (H2D, compute, D2H) with double-buffered device staging: while chunk c runs on the tensor
-    cores, chunk c+1 is crossing PCIe and chunk c-1's output is going back.  This is the call bench.py's
-    `e2e` figure times.  Device staging is allocated once here, never per call.
+    Thin wrapper over the native C-ABI pipeline (`fa_b200_host_ctx_create` / `fa_b200_forward_host`,
+    csrc/fa_host.cu): the (b,h) slices are independent, so one forward is cut into `chunks` groups of slices and
+    pipelined on three streams (H2D, compute, D2H) through double-buffered device staging that the context owns:
+    while chunk c runs on the tensor cores, chunk c+1 is crossing PCIe and chunk c-1's output is going back.
+    This is the call bench.py's `e2e` figure times.
     """
 
     def __init__(self, B: int, H: int, N: int, d: int, dtype: torch.dtype, causal: bool = False,
                  chunks: int = 8, device=None):
         self.device = torch.device(device if device is not None else torch.cuda.current_device())
-        self.BH, self.N, self.d, self.dtype, self.causal = B * H, N, d, dtype, causal
-        chunks = max(1, min(chunks, self.BH))
-        base, rem = divmod(self.BH, chunks)
-        self.ranges, s = [], 0
-        for c in range(chunks):
-            n = base + (1 if c < rem else 0)
-            self.ranges.append((s, s + n))
-            s += n
-        cmax = base + (1 if rem else 0)
+        self.B, self.H, self.N, self.d, self.dtype, self.causal = B, H, N, d, dtype, causal
+        code = FA_B200_FP16 if dtype == torch.float16 else FA_B200_BF16 if dtype == torch.bfloat16 else None
+        if code is None:
+            raise TypeError(f"unsupported dtype {dtype}: fp16 or bf16 required")
+        self._ctx = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            mk = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, device=self.device)
-            self.slots = [dict(q=mk(1, cmax, N, d), k=mk(1, cmax, N, d), v=mk(1, cmax, N, d), o=mk(1, cmax, N, d),
-                               lse=mk(1, cmax, N, dt=torch.float32)) for _ in range(2)]
-            self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(self.device) for _ in range(3))
-            self.ev_in_free = [None, None]    # compute of the chunk that last used the slot's inputs
-            self.ev_out_free = [None, None]   # D2H of the chunk that last used the slot's outputs
+            _lib.check(_lib.load().fa_b200_host_ctx_create(B, H, N, d, code, 1 if causal else 0, chunks,
+                                                           ctypes.byref(self._ctx)))
 
     def bytes_per_call(self) -> Tuple[int, int]:
         e = torch.empty((), dtype=self.dtype).element_size()
-        n = self.BH * self.N * self.d
-        return 3 * n * e, n * e + self.BH * self.N * 4
+        n = self.B * self.H * self.N * self.d
+        return 3 * n * e, n * e + self.B * self.H * self.N * 4
 
-    def __call__(self, q_host, k_host, v_host, o_host, lse_host):
-        """All five are pinned CPU tensors: q,k,v,o `[B,H,N,d]` dtype, lse `[B,H,N]` fp32."""
-        for t in (q_host, k_host, v_host, o_host, lse_host):
-            if t.is_cuda or not t.is_pinned():
-                raise ValueError("HostPipeline expects pinned host tensors")
-        N, d = self.N, self.d
-        qh, kh, vh, oh = (t.view(1, self.BH, N, d) for t in (q_host, k_host, v_host, o_host))
-        lh = lse_host.view(1, self.BH, N)
+    def __call__(self, q_host, k_host, v_host, o_host, lse_host=None):
+        """q,k,v,o: pinned CPU tensors `[B,H,N,d]` of the context's dtype; lse: pinned fp32 `[B,H,N]` or None.
+        Enqueues one forward and returns; call synchronize() before reading o_host / lse_host."""
+        shape = (self.B, self.H, self.N, self.d)
+        for t in (q_host, k_host, v_host, o_host):
+            if t.is_cuda or not t.is_pinned() or not t.is_contiguous() or tuple(t.shape) != shape or t.dtype != self.dtype:
+                raise ValueError("HostPipeline expects contiguous pinned host tensors [B,H,N,d] of the context's dtype")
+        if lse_host is not None and (lse_host.is_cuda or not lse_host.is_pinned() or not lse_host.is_contiguous()
+                                     or lse_host.dtype != torch.float32 or tuple(lse_host.shape) != shape[:3]):
+            raise ValueError("lse_host must be a contiguous pinned fp32 [B,H,N] tensor")
         with torch.cuda.device(self.device):
-            for c, (b, e) in enumerate(self.ranges):
-                n, slot = e - b, self.slots[c % 2]
-                with torch.cuda.stream(self.s_h2d):
-                    if self.ev_in_free[c % 2] is not None:
-                        self.s_h2d.wait_event(self.ev_in_free[c % 2])
-                    slot["q"][:, :n].copy_(qh[:, b:e], non_blocking=True)
-                    slot["k"][:, :n].copy_(kh[:, b:e], non_blocking=True)
-                    slot["v"][:, :n].copy_(vh[:, b:e], non_blocking=True)
-                    ev_in = torch.cuda.Event()
-                    ev_in.record(self.s_h2d)
-                with torch.cuda.stream(self.s_comp):
-                    self.s_comp.wait_event(ev_in)
-                    if self.ev_out_free[c % 2] is not None:
-                        self.s_comp.wait_event(self.ev_out_free[c % 2])
-                    attention_forward(slot["q"][:, :n], slot["k"][:, :n], slot["v"][:, :n], causal=self.causal,
-                                      out=slot["o"][:, :n], lse=slot["lse"][:, :n])
-                    ev_c = torch.cuda.Event()
-                    ev_c.record(self.s_comp)
-                    self.ev_in_free[c % 2] = ev_c
-                with torch.cuda.stream(self.s_d2h):
-                    self.s_d2h.wait_event(ev_c)
-                    oh[:, b:e].copy_(slot["o"][:, :n], non_blocking=True)
-                    lh[:, b:e].copy_(slot["lse"][:, :n], non_blocking=True)
-                    ev_o = torch.cuda.Event()
-                    ev_o.record(self.s_d2h)
-                    self.ev_out_free[c % 2] = ev_o
+            _lib.check(_lib.load().fa_b200_forward_host(self._ctx, q_host.data_ptr(), k_host.data_ptr(),
+                                                        v_host.data_ptr(), o_host.data_ptr(),
+                                                        lse_host.data_ptr() if lse_host is not None else None))
         return o_host, lse_host
 
     def synchronize(self):
-        self.s_d2h.synchronize()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().fa_b200_host_ctx_sync(self._ctx))
+
+    def elapsed_ms_last_call(self) -> float:
+        """Device time between the first H2D copy and the end of the last D2H copy of the most recent call
+        (CUDA events recorded inside fa_b200_forward_host); call after synchronize()."""
+        ms = ctypes.c_float(0.0)
+        _lib.check(_lib.load().fa_b200_host_ctx_elapsed_ms(self._ctx, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            _lib.load().fa_b200_host_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

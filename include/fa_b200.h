@@ -105,6 +105,23 @@ int fa_b200_merge_partial(float* O_acc, float* lse_acc, const void* O_part, cons
 /* Final cast of the fp32 ring accumulator to dtype: O[rows,d] = (dtype) O_acc[rows,d]. */
 int fa_b200_cast_output(void* O, const float* O_acc, int64_t rows, int d, int dtype, void* stream);
 
+/* ---- host-buffer path (what bench.py's `e2e` figure times) -------------------------------------------------
+ * The reference's drivers keep Q, K, V on the host and copy them over before launching (main.cu:403-405,
+ * test_flash_attn.cu:86-104).  This is that path as one call: pinned host Q,K,V -> device -> kernel -> pinned host
+ * O (+ lse).  The (b,h) slices are independent, so the work is cut into `chunks` groups of slices and pipelined
+ * on three streams (H2D / compute / D2H) through double-buffered device staging owned by the context; staging is
+ * allocated once in fa_b200_host_ctx_create, never per call.  fa_b200_forward_host() enqueues one whole forward
+ * and returns; fa_b200_host_ctx_sync() waits for everything enqueued on the context. */
+typedef struct fa_b200_host_ctx fa_b200_host_ctx;
+int fa_b200_host_ctx_create(int B, int H, int N, int d, int dtype, int causal, int chunks, fa_b200_host_ctx** out);
+int fa_b200_forward_host(fa_b200_host_ctx* ctx, const void* q_host, const void* k_host, const void* v_host,
+                         void* o_host, float* lse_host /* may be NULL */);
+int fa_b200_host_ctx_sync(fa_b200_host_ctx* ctx);
+/* Device time (CUDA events) from the first H2D copy to the end of the last D2H copy of the most recent
+ * fa_b200_forward_host call; call after fa_b200_host_ctx_sync. */
+int fa_b200_host_ctx_elapsed_ms(fa_b200_host_ctx* ctx, float* ms);
+void fa_b200_host_ctx_destroy(fa_b200_host_ctx* ctx);
+
 /* Introspection of the tile scheduler (host-only, no GPU needed): decodes work item `index` of the launch that
  * fa_b200_forward would make for this shape - which (b*H+h) slice, first query row, and how many 128-key K/V
  * tiles each of its two 128-row Q tiles visits (0 = tile skipped).  Returns the number of work items

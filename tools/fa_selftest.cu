@@ -5,6 +5,7 @@
 //   fa_selftest attn B H N d dtype(0=fp16,1=bf16) causal [N_kv] [set(R|S)] [iters]
 //   fa_selftest umma D [lbo_v sbo_v kstep_v_bytes lbo_qk sbo_qk]
 //   fa_selftest ref  B H N d M            (reference FA1 kernel from oracle/_ref vs library, fp16)
+//   fa_selftest host B H N d dtype causal [chunks] [iters]   (C-ABI host-buffer pipeline vs device path)
 //
 // Test infrastructure only: the oracle is the checker here, never the thing measured.
 #include <cuda.h>
@@ -195,6 +196,52 @@ static int run_attn(int argc, char** argv) {
            fl / ts[0] * 1e-9);
   }
   return pass ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------ host
+// C-ABI host-buffer pipeline (fa_b200_forward_host) vs the device-resident path: must be bit-identical.
+static int run_host(int argc, char** argv) {
+  if (argc < 8) { fprintf(stderr, "usage: host B H N d dtype causal [chunks] [iters]\n"); return 2; }
+  const int B = atoi(argv[2]), H = atoi(argv[3]), N = atoi(argv[4]), d = atoi(argv[5]);
+  const int dtype = atoi(argv[6]), causal = atoi(argv[7]);
+  const int chunks = argc > 8 ? atoi(argv[8]) : 8, iters = argc > 9 ? atoi(argv[9]) : 3;
+  const bool bf16 = dtype == 1;
+  const size_t n = (size_t)B * H * N * d, ns = (size_t)B * H * N;
+  std::vector<float> q(n), k(n), v(n);
+  fixture_normal_bf16(q.data(), n, 1, 1.f); fixture_normal_bf16(k.data(), n, 2, 1.f);
+  fixture_uniform_bf16(v.data(), n, 3, -0.5f, 0.5f);
+  auto q16 = to16(q, bf16), k16 = to16(k, bf16), v16 = to16(v, bf16);
+  void *hq, *hk, *hv, *ho; float* hl;
+  CK(cudaMallocHost(&hq, n * 2)); CK(cudaMallocHost(&hk, n * 2)); CK(cudaMallocHost(&hv, n * 2));
+  CK(cudaMallocHost(&ho, n * 2)); CK(cudaMallocHost((void**)&hl, ns * 4));
+  memcpy(hq, q16.data(), n * 2); memcpy(hk, k16.data(), n * 2); memcpy(hv, v16.data(), n * 2);
+  // device-resident reference run
+  void *dQ, *dK, *dV, *dO; float* dl;
+  CK(cudaMalloc(&dQ, n * 2)); CK(cudaMalloc(&dK, n * 2)); CK(cudaMalloc(&dV, n * 2)); CK(cudaMalloc(&dO, n * 2));
+  CK(cudaMalloc(&dl, ns * 4));
+  CK(cudaMemcpy(dQ, hq, n * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dK, hk, n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dV, hv, n * 2, cudaMemcpyHostToDevice));
+  fa_b200_params p; memset(&p, 0, sizeof(p));
+  p.Q = dQ; p.K = dK; p.V = dV; p.O = dO; p.lse = dl; p.B = B; p.H = H; p.N = N; p.d = d; p.dtype = dtype; p.causal = causal;
+  if (fa_b200_forward(&p)) { printf("RESULT host FAIL %s\n", fa_b200_last_error()); return 1; }
+  CK(cudaDeviceSynchronize());
+  std::vector<uint16_t> oref(n); std::vector<float> lref(ns);
+  CK(cudaMemcpy(oref.data(), dO, n * 2, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(lref.data(), dl, ns * 4, cudaMemcpyDeviceToHost));
+  fa_b200_host_ctx* ctx = nullptr;
+  if (fa_b200_host_ctx_create(B, H, N, d, dtype, causal, chunks, &ctx)) { printf("RESULT host FAIL %s\n", fa_b200_last_error()); return 1; }
+  float best = 1e30f;
+  for (int i = 0; i < iters; ++i) {
+    memset(ho, 0xff, n * 2);
+    if (fa_b200_forward_host(ctx, hq, hk, hv, ho, hl) || fa_b200_host_ctx_sync(ctx)) { printf("RESULT host FAIL %s\n", fa_b200_last_error()); return 1; }
+    float ms = 0; fa_b200_host_ctx_elapsed_ms(ctx, &ms); best = std::min(best, ms);
+  }
+  const bool same = memcmp(ho, oref.data(), n * 2) == 0 && memcmp(hl, lref.data(), ns * 4) == 0;
+  const double fl = 4.0 * B * H * (double)N * N * d * (causal ? 0.5 : 1.0);
+  printf("RESULT host %s B=%d H=%d N=%d d=%d %s causal=%d chunks=%d: bit-identical to the device path: %s; best %.3f ms -> %.1f TFLOP/s end to end (%.1f GB/s H2D)\n",
+         same ? "PASS" : "FAIL", B, H, N, d, bf16 ? "bf16" : "fp16", causal, chunks, same ? "yes" : "NO", best, fl / best * 1e-9,
+         3.0 * n * 2 / best * 1e-6);
+  fa_b200_host_ctx_destroy(ctx);
+  return same ? 0 : 1;
 }
 
 // ------------------------------------------------------------------------------------------ ref
@@ -428,6 +475,7 @@ int main(int argc, char** argv) {
   std::string mode = argv[1];
   if (mode == "attn") return run_attn(argc, argv);
   if (mode == "ref") return run_ref(argc, argv);
+  if (mode == "host") return run_host(argc, argv);
   if (mode == "umma") {
     const int D = argc > 2 ? atoi(argv[2]) : 128;
     return D == 32 ? run_umma_d<32>(argc, argv) : D == 64 ? run_umma_d<64>(argc, argv) : run_umma_d<128>(argc, argv);
