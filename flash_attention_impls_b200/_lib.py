@@ -36,8 +36,10 @@ class FaB200Params(Structure):
         ("lse", c_void_p), ("l", c_void_p), ("m", c_void_p),
         ("B", c_int), ("H", c_int), ("N", c_int), ("d", c_int),
         ("N_kv", c_int), ("dtype", c_int), ("causal", c_int), ("softmax_scale", c_float),
-        ("q_stride_bh", c_int64), ("kv_stride_bh", c_int64), ("o_stride_bh", c_int64),
-        ("stat_stride_bh", c_int64),
+        ("q_stride_b", c_int64), ("q_stride_h", c_int64), ("q_stride_n", c_int64),
+        ("kv_stride_b", c_int64), ("kv_stride_h", c_int64), ("kv_stride_n", c_int64),
+        ("o_stride_b", c_int64), ("o_stride_h", c_int64), ("o_stride_n", c_int64),
+        ("stat_stride_b", c_int64), ("stat_stride_h", c_int64),
         ("stream", c_void_p),
     ]
 

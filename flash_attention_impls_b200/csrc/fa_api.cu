@@ -53,19 +53,37 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [BH, rows, d] tensor, d contiguous, viewed as a 3-D TMA tensor {d, rows, BH}; box = 64 x 128 x 1
-// with the 128-byte swizzle the UMMA descriptors expect.  Out-of-range rows read as zero and are
-// clipped on store, which is what makes ragged N work.
-int make_tmap(CUtensorMap* tm, const void* base, int dtype, int d, int rows, long long bh,
-              long long stride_bh_elems) {
+// [B, H, rows, d] tensor view with element strides (sb, sh, sn), d contiguous, described as a 4-D TMA tensor
+// {d, a1, a2, a3}.  The three outer axes (rows, heads, batch) are sorted by stride so the map's strides ascend
+// (a [B,N,H,d] view has head stride < row stride); *perm records, 2 bits per axis, which of row (0) / head (1) /
+// batch (2) each outer axis carries, and the kernel orders its coordinates accordingly.  The box is
+// 64 columns x 128 rows x 1 x 1 with the 128-byte swizzle the UMMA descriptors expect (d = 32: 32 columns, 64-byte
+// swizzle).  Out-of-range rows read as zero and are clipped on store, which is what makes ragged N work.
+int make_tmap(CUtensorMap* tm, unsigned* perm, const void* base, int dtype, int d, long long rows, long long H,
+              long long B, long long sn, long long sh, long long sb) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, (cuuint64_t)bh};
-  cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)stride_bh_elems * 2};
-  cuuint32_t box[3] = {(cuuint32_t)(d >= 64 ? 64 : 32), 128, 1};   // d = 32: one 64-byte-row box, 64B swizzle
-  cuuint32_t estr[3] = {1, 1, 1};
+  struct Axis { long long size, stride; unsigned role; cuuint32_t box; };
+  Axis ax[3] = {{rows, sn, 0u, 128u}, {H, sh, 1u, 1u}, {B, sb, 2u, 1u}};
+  // insertion sort by stride; size-1 axes go last (their stride is irrelevant and may be anything)
+  auto key = [](const Axis& x) { return x.size == 1 ? (1LL << 62) : x.stride; };
+  for (int i = 1; i < 3; ++i)
+    for (int j = i; j > 0 && key(ax[j]) < key(ax[j - 1]); --j) std::swap(ax[j], ax[j - 1]);
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)ax[0].size, (cuuint64_t)ax[1].size, (cuuint64_t)ax[2].size};
+  cuuint64_t strides[3];
+  cuuint32_t box[4] = {(cuuint32_t)(d >= 64 ? 64 : 32), ax[0].box, ax[1].box, ax[2].box};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  unsigned long long prev_extent = (unsigned long long)d * 2;
+  *perm = 0;
+  for (int i = 0; i < 3; ++i) {
+    // a size-1 axis never advances: give it any legal stride (the extent so far)
+    unsigned long long st = ax[i].size == 1 ? prev_extent : (unsigned long long)ax[i].stride * 2;
+    strides[i] = st;
+    prev_extent = std::max(prev_extent, st * (unsigned long long)ax[i].size);
+    *perm |= ax[i].role << (2 * i);
+  }
   CUresult r = enc(tm, dtype == FA_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                   3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    d >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -205,25 +223,39 @@ int fa_b200_forward(const fa_b200_params* p) {
   const int d = p->d;
   const long long num_q_blocks = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
   if (BH * num_q_blocks > 0x7fffffffLL) return fail(FA_B200_ERR_SHAPE, "B*H*ceil(N/256) exceeds the grid limit");
-  const long long qs = p->q_stride_bh ? p->q_stride_bh : (long long)Nq * d;
-  const long long ks = p->kv_stride_bh ? p->kv_stride_bh : (long long)Nkv * d;
-  const long long os = p->o_stride_bh ? p->o_stride_bh : (long long)Nq * d;
-  const long long ss = p->stat_stride_bh ? p->stat_stride_bh : (long long)Nq;
+  // strides: 0 => dense [B,H,N,d] default
+  struct Str { long long b, h, n; };
+  auto resolve = [&](long long sb, long long sh, long long sn, long long rows) {
+    Str r;
+    r.n = sn ? sn : d;
+    r.h = sh ? sh : rows * r.n;
+    r.b = sb ? sb : (long long)p->H * r.h;
+    return r;
+  };
+  const Str qs = resolve(p->q_stride_b, p->q_stride_h, p->q_stride_n, Nq);
+  const Str ks = resolve(p->kv_stride_b, p->kv_stride_h, p->kv_stride_n, Nkv);
+  const Str os = resolve(p->o_stride_b, p->o_stride_h, p->o_stride_n, Nq);
+  const long long ssh = p->stat_stride_h ? p->stat_stride_h : (long long)Nq;
+  const long long ssb = p->stat_stride_b ? p->stat_stride_b : (long long)p->H * ssh;
   auto mis = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
   if (mis(p->Q) || mis(p->K) || mis(p->V) || mis(p->O))
     return fail(FA_B200_ERR_ALIGNMENT, "Q, K, V, O base pointers must be 16-byte aligned");
-  if ((qs % 8) || (ks % 8) || (os % 8))
-    return fail(FA_B200_ERR_ALIGNMENT, "(b,h) strides must be multiples of 8 elements");
-  if (qs < (long long)Nq * d || ks < (long long)Nkv * d || os < (long long)Nq * d || ss < Nq)
-    return fail(FA_B200_ERR_SHAPE, "(b,h) stride smaller than one slice");
+  for (const Str* t : {&qs, &ks, &os}) {
+    if ((t->b % 8) || (t->h % 8) || (t->n % 8))
+      return fail(FA_B200_ERR_ALIGNMENT, "batch / head / row strides must be multiples of 8 elements");
+    if (t->b <= 0 || t->h <= 0 || t->n < d)
+      return fail(FA_B200_ERR_SHAPE, "strides must be positive and the row stride at least d");
+  }
+  if (ssh < Nq || ssb <= 0) return fail(FA_B200_ERR_SHAPE, "statistics head stride smaller than N");
   int rc = check_device();
   if (rc) return rc;
 
   CUtensorMap tq, tk, tv, to;
-  if ((rc = make_tmap(&tq, p->Q, p->dtype, d, Nq, BH, qs))) return rc;
-  if ((rc = make_tmap(&tk, p->K, p->dtype, d, Nkv, BH, ks))) return rc;
-  if ((rc = make_tmap(&tv, p->V, p->dtype, d, Nkv, BH, ks))) return rc;
-  if ((rc = make_tmap(&to, p->O, p->dtype, d, Nq, BH, os))) return rc;
+  unsigned perm_q = 0, perm_kv = 0, perm_v = 0, perm_o = 0;
+  if ((rc = make_tmap(&tq, &perm_q, p->Q, p->dtype, d, Nq, p->H, p->B, qs.n, qs.h, qs.b))) return rc;
+  if ((rc = make_tmap(&tk, &perm_kv, p->K, p->dtype, d, Nkv, p->H, p->B, ks.n, ks.h, ks.b))) return rc;
+  if ((rc = make_tmap(&tv, &perm_v, p->V, p->dtype, d, Nkv, p->H, p->B, ks.n, ks.h, ks.b))) return rc;
+  if ((rc = make_tmap(&to, &perm_o, p->O, p->dtype, d, Nq, p->H, p->B, os.n, os.h, os.b))) return rc;
 
   const float scale = (p->softmax_scale != 0.f) ? p->softmax_scale : 1.0f / sqrtf((float)d);
   fa::FwdArgs a{};
@@ -232,7 +264,12 @@ int fa_b200_forward(const fa_b200_params* p) {
   a.m = p->m;
   fill_schedule(a, BH, Nq, Nkv, d);
   a.scale_log2 = scale * 1.4426950408889634f;
-  a.stat_stride_bh = ss;
+  a.stat_stride_b = ssb;
+  a.stat_stride_h = ssh;
+  a.H = p->H;
+  a.perm_q = perm_q;
+  a.perm_kv = perm_kv;
+  a.perm_o = perm_o;
   const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;
   if (d >= 64) {
     // Q, K: K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.

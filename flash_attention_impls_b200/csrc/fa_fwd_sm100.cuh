@@ -45,7 +45,11 @@ struct FwdArgs {
   int num_bh;       // B*H
   int group_heads;  // causal item ordering: heads per L2-sized group (see get_item)
   float scale_log2; // softmax_scale * log2(e)
-  long long stat_stride_bh;
+  long long stat_stride_b, stat_stride_h;
+  int H;            // heads per batch (a work item's bh is split into (b, h) for the 4-D tensor maps)
+  // Order of the three outer tensor-map axes for Q, K/V and O: axis k of the map carries the row (0), head (1) or
+  // batch (2) coordinate, 2 bits each (the host sorts the axes by stride, see make_tmap).
+  unsigned int perm_q, perm_kv, perm_o;
   unsigned long long desc_hi_qk;  // K-major 128B-swizzle descriptor bits (Q, K)
   unsigned long long desc_hi_v;   // MN-major 128B-swizzle descriptor bits (V)
   unsigned int idesc_qk, idesc_pv;
@@ -133,6 +137,18 @@ __device__ __forceinline__ float2 ex2_emulated(float2 x) {
 #ifndef FA_EMU_PAIRS_OF_4
 #define FA_EMU_PAIRS_OF_4 0
 #endif
+
+// Tensor maps are 4-D {d, a1, a2, a3}; `perm` says which of (row, head, batch) each outer axis carries.
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int col, int row,
+                                              int h, int b, unsigned int perm) {
+  auto pick = [&](unsigned int r) { return r == 0u ? row : (r == 1u ? h : b); };
+  tma_load_4d(dst, tm, bar, col, pick(perm & 3u), pick((perm >> 2) & 3u), pick((perm >> 4) & 3u));
+}
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, uint32_t src, int col, int row, int h, int b,
+                                               unsigned int perm) {
+  auto pick = [&](unsigned int r) { return r == 0u ? row : (r == 1u ? h : b); };
+  tma_store_4d(tm, src, col, pick(perm & 3u), pick((perm >> 2) & 3u), pick((perm >> 4) & 3u));
+}
 
 // One work item = 256 query rows of one (b,h).  Every role walks the same deterministic item list.
 struct WorkItem {
@@ -297,15 +313,17 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             a.trace[4096 + (blockIdx.x * 40 + t) * 2 + 1] = (long long)now;
           }
 #endif
-          auto load_tile = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int row0) {
+          const int b_idx = wi.bh / a.H, h_idx = wi.bh - b_idx * a.H;
+          auto load_tile = [&](const CUtensorMap* tm, unsigned int perm, uint32_t dst, uint32_t bar, int row0) {
             mbar_arrive_expect_tx(bar, kTileBytes);
 #pragma unroll
-            for (int h = 0; h < kNumBoxes; ++h) tma_load_3d(dst + h * kBoxBytes, tm, bar, h * kBoxCols, row0, wi.bh);
+            for (int h = 0; h < kNumBoxes; ++h)
+              tma_load_tile(dst + h * kBoxBytes, tm, bar, h * kBoxCols, row0, h_idx, b_idx, perm);
           };
           // Q_i of the previous item must have been consumed by all of its QK^T MMAs
           if (wi.n_t0 > 0) {
             mbar_wait(bar_q_empty, (nq[0] & 1u) ^ 1u, 110);
-            load_tile(&tmQ, sQ, bar_q_full, wi.q0);
+            load_tile(&tmQ, a.perm_q, sQ, bar_q_full, wi.q0);
             ++nq[0];
           }
           for (int j = 0; j < wi.n_max; ++j) {
@@ -314,11 +332,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               const int stage = it % kStages;
               const uint32_t ph = (it / kStages) & 1;
               mbar_wait(bar_kv_empty + 8 * stage, ph ^ 1, 100 + kv);
-              load_tile(kv == 0 ? &tmK : &tmV, sKV + stage * kTileBytes, bar_kv_full + 8 * stage, j * kBlockN);
+              load_tile(kv == 0 ? &tmK : &tmV, a.perm_kv, sKV + stage * kTileBytes, bar_kv_full + 8 * stage, j * kBlockN);
               ++it;
               if (j == 0 && kv == 0 && wi.n_t1 > 0) {
                 mbar_wait(bar_q_empty + 8, (nq[1] & 1u) ^ 1u, 111);
-                load_tile(&tmQ, sQ + kTileBytes, bar_q_full + 8, wi.q0 + kBlockM);
+                load_tile(&tmQ, a.perm_q, sQ + kTileBytes, bar_q_full + 8, wi.q0 + kBlockM);
                 ++nq[1];
               }
             }
@@ -511,7 +529,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (row_in_tile == 0) {
 #pragma unroll
           for (int h = 0; h < kNumBoxes; ++h)
-            tma_store_3d(&tmO, sO + h * kBoxBytes, h * kBoxCols, wi.q0 + i * kBlockM, wi.bh);
+            tma_store_tile(&tmO, sO + h * kBoxBytes, h * kBoxCols, wi.q0 + i * kBlockM, wi.bh % a.H, wi.bh / a.H, a.perm_o);
           tma_store_commit();
         }
         store_pending = true;
@@ -659,7 +677,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const WorkItem wi = get_item<kCausal>(a, w_cur);   // recomputed here to keep it out of the hot loop's registers
       const int row = wi.q0 + i * kBlockM + row_in_tile;
       if (row < a.Nq) {
-        const long long off = (long long)wi.bh * a.stat_stride_bh + row;
+        const long long off = (long long)(wi.bh / a.H) * a.stat_stride_b + (long long)(wi.bh % a.H) * a.stat_stride_h + row;
         const float ln2 = 0.6931471805599453f;
         const bool any = l > 0.f;
         if (a.lse) a.lse[off] = any ? fmaf(m_ref, ln2, logf(l)) : -INFINITY;

@@ -45,8 +45,10 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
                       m: Optional[torch.Tensor] = None, return_lse: bool = True):
     """O = softmax(Q K^T * scale [+ causal mask]) V on [B,H,N,d] tensors; returns (O, lse).
 
-    q: [B,H,N,d]; k, v: [B,H,N_kv,d]; fp16 or bf16, last dim contiguous, rows dense (stride d); the
-    (b,h) slices may be strided views of a longer sequence (what the ring driver passes).
+    q: [B,H,N,d]; k, v: [B,H,N_kv,d]; fp16 or bf16.  Only the last dim has to be contiguous: batch, head and row
+    strides are passed to the kernel's TMA descriptors as they are (multiples of 8 elements), so row sub-ranges of
+    a longer sequence (what the ring driver passes) and `x.transpose(1, 2)` views of [B,N,H,d] tensors need no copy.
+    k and v must share their strides.
     """
     _require_cuda(q, k, v)
     if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
@@ -59,30 +61,32 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
         raise TypeError("q, k, v must share a dtype")
     dtype = _dtype_code(q)
 
-    def bh_stride(t: torch.Tensor, rows: int, what: str) -> int:
-        if t.stride(3) != 1 or t.stride(2) != t.shape[3]:
-            raise ValueError(f"{what}: rows must be dense (stride(-1)=1, stride(-2)=d); call .contiguous()")
-        if H > 1 and B > 1 and t.stride(0) != t.stride(1) * H:
-            raise ValueError(f"{what}: batch and head strides must collapse to one (b*H+h) stride")
-        return t.stride(1) if H > 1 else (t.stride(0) if B > 1 else rows * t.shape[3])
+    def strides(t: torch.Tensor, what: str):
+        if t.stride(3) != 1:
+            raise ValueError(f"{what}: the last dimension must be contiguous; call .contiguous()")
+        # size-1 axes report arbitrary strides in torch: give the kernel the dense default (0) for those
+        return tuple(t.stride(i) if t.shape[i] > 1 else 0 for i in range(3))
 
-    qs, ks, vs = bh_stride(q, N, "q"), bh_stride(k, Nkv, "k"), bh_stride(v, Nkv, "v")
+    qs, ks, vs = strides(q, "q"), strides(k, "k"), strides(v, "v")
     if ks != vs:
-        raise ValueError("k and v must share their (b,h) stride")
+        raise ValueError("k and v must share their strides")
     if out is None:
         out = torch.empty((B, H, N, d), dtype=q.dtype, device=q.device)
-    os_ = bh_stride(out, N, "out")
+    if out.shape != (B, H, N, d) or out.dtype != q.dtype:
+        raise ValueError("out must be [B,H,N,d] of q's dtype")
+    os_ = strides(out, "out")
     if lse is None and return_lse:
         lse = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
-    ss = 0
-    for s in (lse, l, m):
-        if s is not None:
-            if s.dtype != torch.float32 or s.shape != (B, H, N) or s.stride(2) != 1:
-                raise ValueError("lse / l / m must be fp32 [B,H,N] with dense rows")
-            st = s.stride(1) if H > 1 else (s.stride(0) if B > 1 else N)
-            if ss and st != ss:
-                raise ValueError("lse, l and m must share their (b,h) stride")
+    ss = None
+    for s_ in (lse, l, m):
+        if s_ is not None:
+            if s_.dtype != torch.float32 or s_.shape != (B, H, N) or (N > 1 and s_.stride(2) != 1):
+                raise ValueError("lse / l / m must be fp32 [B,H,N] with contiguous rows")
+            st = tuple(s_.stride(i) if s_.shape[i] > 1 else 0 for i in range(2))
+            if ss is not None and st != ss:
+                raise ValueError("lse, l and m must share their strides")
             ss = st
+    ss = ss or (0, 0)
 
     p = FaB200Params()
     p.Q, p.K, p.V, p.O = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
@@ -94,7 +98,10 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
     p.dtype = dtype
     p.causal = 1 if causal else 0
     p.softmax_scale = float(softmax_scale) if softmax_scale else 0.0
-    p.q_stride_bh, p.kv_stride_bh, p.o_stride_bh, p.stat_stride_bh = qs, ks, os_, ss
+    p.q_stride_b, p.q_stride_h, p.q_stride_n = qs
+    p.kv_stride_b, p.kv_stride_h, p.kv_stride_n = ks
+    p.o_stride_b, p.o_stride_h, p.o_stride_n = os_
+    p.stat_stride_b, p.stat_stride_h = ss
     p.stream = _stream_ptr(q)
     with torch.cuda.device(q.device):
         _lib.check(_lib.load().fa_b200_forward(ctypes.byref(p)))

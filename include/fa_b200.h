@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define FA_B200_VERSION_MAJOR 0
-#define FA_B200_VERSION_MINOR 1
+#define FA_B200_VERSION_MINOR 2
 
 /* status codes (0 = ok).  The reference returns void and prints to stderr
  * (flash_attn_cutlass.cu:540-542, :510-514); the C ABI returns codes instead. */
@@ -71,10 +71,17 @@ typedef struct fa_b200_params {
   int causal;        /* 0 / 1.  Mask rule col > row + (N_kv - N) -> -inf; with N_kv == N this is
                         FA2-triton.py:70-73 (square, top-left aligned) */
   float softmax_scale; /* 0 => 1/sqrt(d) (flashAttention.cu:96, flash_attn_cutlass.cu:470) */
-  /* Element strides between consecutive (b*H+h) slices; 0 => dense (N*d, N_kv*d, N*d, N).
-   * Rows are always d-contiguous.  Lets a caller pass row sub-ranges of a longer sequence
-   * (used by the ring-attention driver). */
-  int64_t q_stride_bh, kv_stride_bh, o_stride_bh, stat_stride_bh;
+  /* Element strides of the batch, head and row (sequence) axes; the d axis is always contiguous.  A stride left
+   * 0 takes its dense [B,H,N,d] default (row: d, head: N*d, batch: H*N*d; statistics: head N, batch H*N), so a
+   * zeroed block means the reference's layout (flashAttention.cu:30).  Non-default strides describe views:
+   * row sub-ranges of a longer sequence (the ring driver), or a [B,N,H,d] tensor (row stride H*d, head stride
+   * d) without a copy - the reference's Triton path takes arbitrary strides the same way
+   * (FA2-triton.py:190-195).  K and V share their strides; lse, l and m share theirs (rows contiguous).
+   * Every stride must be a multiple of 8 elements (TMA: 16 bytes). */
+  int64_t q_stride_b, q_stride_h, q_stride_n;
+  int64_t kv_stride_b, kv_stride_h, kv_stride_n;
+  int64_t o_stride_b, o_stride_h, o_stride_n;
+  int64_t stat_stride_b, stat_stride_h;
   void* stream;      /* cudaStream_t; NULL => legacy default stream, as in the reference */
 } fa_b200_params;
 

@@ -42,13 +42,13 @@ def test_reference_named_cxx_shims_are_exported():
 
 
 def test_struct_layout_matches_header():
-    # 7 pointers, 7 ints + float, 4 int64, 1 pointer  (x86-64 LP64)
-    assert ctypes.sizeof(_lib.FaB200Params) == 7 * 8 + 8 * 4 + 4 * 8 + 8
+    # 7 pointers, 7 ints + float, 11 int64 strides, 1 pointer  (x86-64 LP64)
+    assert ctypes.sizeof(_lib.FaB200Params) == 7 * 8 + 8 * 4 + 11 * 8 + 8
 
 
 def test_version_and_status_strings():
     lib = _lib.load()
-    assert lib.fa_b200_version() == (0 << 16) | 1
+    assert lib.fa_b200_version() == (0 << 16) | 2
     assert lib.fa_b200_status_string(0) == b"ok"
     assert lib.fa_b200_status_string(3) == b"unsupported head_dim"
     assert lib.fa_b200_status_string(99) == b"unknown status"
@@ -66,7 +66,8 @@ def _params(**kw):
 @pytest.mark.parametrize("kw,status", [
     (dict(Q=None), 1), (dict(O=None), 1), (dict(B=0), 2), (dict(N=-5), 2), (dict(N_kv=-1), 2),
     (dict(d=48), 3), (dict(d=96), 3), (dict(d=256), 3), (dict(dtype=7), 4),
-    (dict(Q=0x1008), 5), (dict(q_stride_bh=8 * 1024 + 4), 5), (dict(q_stride_bh=64), 2),
+    (dict(Q=0x1008), 5), (dict(q_stride_h=8 * 1024 + 4), 5), (dict(o_stride_n=68), 5), (dict(q_stride_n=32), 2),
+    (dict(stat_stride_h=64), 2),
 ])
 def test_argument_validation_returns_codes_without_a_gpu(kw, status):
     """Error convention of SURVEY.md section 8b: an int status instead of the reference's stderr +

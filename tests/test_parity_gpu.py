@@ -232,6 +232,51 @@ def test_strided_bh_views(fa):
     assert torch.all(out[:, :, :256] == 0) and torch.all(torch.isinf(lse[:, :, :256]))   # untouched rows
 
 
+@pytest.mark.parametrize("d,dtype,causal", [(128, "bf16", True), (64, "fp16", False), (32, "bf16", True)])
+def test_bnhd_layout_views_without_copy(fa, d, dtype, causal):
+    """[B,N,H,d] tensors passed as transpose(1,2) views: row stride H*d, head stride d (the reference's Triton path
+    takes arbitrary strides the same way, FA2-triton.py:190-195).  Output written into a [B,N,H,d] buffer too."""
+    from oracle import oracle
+    B, H, N = 2, 3, 700
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d), seeds=(51, 52, 53))
+    dev = torch.device("cuda:0")
+    dt = _dt(dtype)
+    # build the [B,N,H,d] storage, then view it as [B,H,N,d]
+    qb, kb, vb = (torch.from_numpy(x).to(dev, dt).transpose(1, 2).contiguous() for x in (q, k, v))
+    assert qb.shape == (B, N, H, d)
+    ob = torch.empty_like(qb)
+    lse_b = torch.empty((B, N, H), dtype=torch.float32, device=dev).transpose(1, 2)   # non-contiguous rows: rejected
+    with pytest.raises(ValueError):
+        fa.attention_forward(qb.transpose(1, 2), kb.transpose(1, 2), vb.transpose(1, 2), causal=causal, lse=lse_b)
+    o, lse = fa.attention_forward(qb.transpose(1, 2), kb.transpose(1, 2), vb.transpose(1, 2), causal=causal,
+                                  out=ob.transpose(1, 2))
+    torch.cuda.synchronize()
+    assert o.data_ptr() == ob.data_ptr() and not o.is_contiguous()
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v, causal=causal)
+    _check(ob.transpose(1, 2).float().cpu().numpy(), lse.cpu().numpy(), o_ref, lse_ref)
+    # and bit-identical to the dense-layout launch
+    o2, lse2 = fa.attention_forward(*(torch.from_numpy(x).to(dev, dt) for x in (q, k, v)), causal=causal)
+    assert torch.equal(o2, ob.transpose(1, 2)) and torch.equal(lse2, lse)
+
+
+def test_batch_strided_views(fa):
+    """Independent batch / head / row strides: a [B,H,N,d] window cut out of a larger allocation in all three axes."""
+    from oracle import oracle
+    B, H, N, d = 2, 2, 300, 64
+    big = torch.zeros((B + 1, H + 2, N + 60, d), dtype=torch.bfloat16, device="cuda:0")
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d), seeds=(61, 62, 63))
+    views = []
+    for x in (q, k, v):
+        buf = big.clone()
+        win = buf[1:, 1:3, 20:20 + N]
+        win.copy_(torch.from_numpy(x))
+        views.append(win)
+    o, lse = fa.attention_forward(*views, causal=True)
+    torch.cuda.synchronize()
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v, causal=True)
+    _check(o.float().cpu().numpy(), lse.cpu().numpy(), o_ref, lse_ref)
+
+
 def test_merge_partial_kernel(fa):
     """attention over [K1;K2] == merge(attention(K1), attention(K2)) (the ring-attention identity)."""
     from oracle import oracle
