@@ -22,7 +22,7 @@ STATUS = {
 
 # every symbol include/fa_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
-    "fa_b200_forward", "fa_b200_forward_legacy", "fa_b200_forward_fp16", "fa_b200_merge_partial",
+    "fa_b200_forward", "fa_b200_workspace_bytes", "fa_b200_forward_legacy", "fa_b200_forward_fp16", "fa_b200_merge_partial",
     "fa_b200_cast_output", "fa_b200_host_ctx_create", "fa_b200_forward_host", "fa_b200_host_ctx_sync",
     "fa_b200_host_ctx_elapsed_ms", "fa_b200_host_ctx_destroy", "fa_b200_work_item", "fa_b200_launch_count", "fa_b200_last_error", "fa_b200_status_string",
     "fa_b200_version",
@@ -41,6 +41,7 @@ class FaB200Params(Structure):
         ("o_stride_b", c_int64), ("o_stride_h", c_int64), ("o_stride_n", c_int64),
         ("stat_stride_b", c_int64), ("stat_stride_h", c_int64),
         ("stream", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", ctypes.c_size_t),
     ]
 
 
@@ -66,6 +67,8 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     lib.fa_b200_forward.argtypes = [POINTER(FaB200Params)]
     lib.fa_b200_forward.restype = c_int
+    lib.fa_b200_workspace_bytes.argtypes = [c_int] * 5
+    lib.fa_b200_workspace_bytes.restype = ctypes.c_size_t
     lib.fa_b200_forward_legacy.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.fa_b200_forward_legacy.restype = c_int

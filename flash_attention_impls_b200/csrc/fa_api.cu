@@ -21,6 +21,13 @@
 #include "../../include/fa_b200.h"
 #include "fa_fwd_sm100.cuh"
 
+namespace fa {
+int launch_split_combine(const void* O_part, const float* lse_part, const float* m_part, void* O, float* lse,
+                         float* l, float* m, int nsplit, long long rows, int d, int H, int N, long long o_sb,
+                         long long o_sh, long long o_sn, long long st_sb, long long st_sh, int dtype,
+                         cudaStream_t stream);
+}
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -167,6 +174,32 @@ unsigned long long env_u64(const char* name, unsigned long long dflt) {
   return s ? strtoull(s, nullptr, 0) : dflt;
 }
 
+// Split-KV policy: how many key-axis splits for a launch with `items` work items of `n_kv_tiles` K/V tiles each.
+int choose_nsplit(long long items, int n_kv_tiles, int sms) {
+  if (items * 2 > sms || n_kv_tiles < 8) return 1;          // enough parallelism already, or too short to split
+  long long n = sms / items;                                 // fill the machine once
+  n = std::min<long long>(n, n_kv_tiles / 4);                // at least 4 tiles per split
+  n = std::min<long long>(n, 32);
+  n = (long long)env_u64("FA_B200_NSPLIT", (unsigned long long)n);
+  return (int)std::max<long long>(1, std::min<long long>(n, n_kv_tiles));
+}
+
+size_t split_workspace_bytes(int nsplit, long long rows, int d) {
+  return nsplit <= 1 ? 0 : (size_t)nsplit * rows * ((size_t)d * 2 + 2 * sizeof(float));
+}
+
+int sm_count() {
+  static std::atomic<int> cache{0};
+  int n = cache.load();
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;   // B200
+    cache.store(n);
+  }
+  return n;
+}
+
 // Shape / scheduling part of the kernel arguments (shared by the launch path and fa_b200_work_item).
 void fill_schedule(fa::FwdArgs& a, long long BH, int Nq, int Nkv, int d) {
   const long long num_q_blocks = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
@@ -183,6 +216,17 @@ void fill_schedule(fa::FwdArgs& a, long long BH, int Nq, int Nkv, int d) {
   a.group_heads = (int)env_u64("FA_B200_GROUP_HEADS", (unsigned long long)g);
   if (a.group_heads < 1) a.group_heads = 1;
   if (a.group_heads > BH) a.group_heads = (int)BH;
+  a.nsplit = 1;
+  a.tiles_per_split = (Nkv + fa::kBlockN - 1) / fa::kBlockN;
+}
+
+// Switch the schedule to `nsplit` key-axis splits.
+void apply_split(fa::FwdArgs& a, int nsplit, int B) {
+  const int n_kv_tiles = (a.Nkv + fa::kBlockN - 1) / fa::kBlockN;
+  a.nsplit = nsplit;
+  a.tiles_per_split = (n_kv_tiles + nsplit - 1) / nsplit;
+  a.num_items *= nsplit;
+  a.B = B;
 }
 
 }  // namespace
@@ -207,6 +251,14 @@ int fa_b200_work_item(int B, int H, int N, int N_kv, int d, int causal, int inde
   if (tiles0) *tiles0 = wi.n_t0;
   if (tiles1) *tiles1 = wi.n_t1;
   return a.num_items;
+}
+
+size_t fa_b200_workspace_bytes(int B, int H, int N, int N_kv, int d) {
+  if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || (d != 32 && d != 64 && d != 128)) return 0;
+  const int Nkv = N_kv ? N_kv : N;
+  const long long items = (long long)B * H * ((N + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM));
+  const int nsplit = choose_nsplit(items, (Nkv + fa::kBlockN - 1) / fa::kBlockN, sm_count());
+  return split_workspace_bytes(nsplit, (long long)B * H * N, d);
 }
 
 int fa_b200_forward(const fa_b200_params* p) {
@@ -250,12 +302,28 @@ int fa_b200_forward(const fa_b200_params* p) {
   int rc = check_device();
   if (rc) return rc;
 
+  // split-KV: only with a large enough caller-provided workspace
+  const long long rows_total = BH * Nq;
+  int nsplit = choose_nsplit(BH * num_q_blocks, (Nkv + fa::kBlockN - 1) / fa::kBlockN, sm_count());
+  if (nsplit > 1 && (!p->workspace || p->workspace_bytes < split_workspace_bytes(nsplit, rows_total, d) ||
+                     (reinterpret_cast<uintptr_t>(p->workspace) & 15u)))
+    nsplit = 1;
+  char* ws_o = static_cast<char*>(p->workspace);
+  float* ws_lse = nsplit > 1 ? reinterpret_cast<float*>(ws_o + (size_t)nsplit * rows_total * d * 2) : nullptr;
+  float* ws_m = nsplit > 1 ? ws_lse + (size_t)nsplit * rows_total : nullptr;
+
   CUtensorMap tq, tk, tv, to;
   unsigned perm_q = 0, perm_kv = 0, perm_v = 0, perm_o = 0;
   if ((rc = make_tmap(&tq, &perm_q, p->Q, p->dtype, d, Nq, p->H, p->B, qs.n, qs.h, qs.b))) return rc;
   if ((rc = make_tmap(&tk, &perm_kv, p->K, p->dtype, d, Nkv, p->H, p->B, ks.n, ks.h, ks.b))) return rc;
   if ((rc = make_tmap(&tv, &perm_v, p->V, p->dtype, d, Nkv, p->H, p->B, ks.n, ks.h, ks.b))) return rc;
-  if ((rc = make_tmap(&to, &perm_o, p->O, p->dtype, d, Nq, p->H, p->B, os.n, os.h, os.b))) return rc;
+  if (nsplit > 1) {   // partial O goes to the dense workspace [nsplit*B, H, N, d]
+    if ((rc = make_tmap(&to, &perm_o, ws_o, p->dtype, d, Nq, p->H, (long long)nsplit * p->B, d, (long long)Nq * d,
+                        (long long)p->H * Nq * d)))
+      return rc;
+  } else if ((rc = make_tmap(&to, &perm_o, p->O, p->dtype, d, Nq, p->H, p->B, os.n, os.h, os.b))) {
+    return rc;
+  }
 
   const float scale = (p->softmax_scale != 0.f) ? p->softmax_scale : 1.0f / sqrtf((float)d);
   fa::FwdArgs a{};
@@ -293,10 +361,18 @@ int fa_b200_forward(const fa_b200_params* p) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
   // one CTA per work item; resident CTAs steal the not-yet-launched ones (cluster launch control), so the
   // kernel behaves as a persistent kernel with a dynamic hardware scheduler
-  const long long grid = BH * num_q_blocks;
+  if (nsplit > 1) {
+    apply_split(a, nsplit, p->B);
+    a.lse = ws_lse;
+    a.m = ws_m;
+    a.l = nullptr;
+    a.stat_stride_h = Nq;
+    a.stat_stride_b = (long long)p->H * Nq;
+  }
+  const long long grid = a.num_items;
   const bool bf16 = p->dtype == FA_B200_BF16;
   const bool causal = p->causal != 0;
-#define FA_LAUNCH(D_, BF_, C_) return launch<D_, BF_, C_>(tq, tk, tv, to, a, grid, stream)
+#define FA_LAUNCH(D_, BF_, C_) rc = launch<D_, BF_, C_>(tq, tk, tv, to, a, grid, stream)
   if (d == 128) {
     if (bf16) { if (causal) FA_LAUNCH(128, true, true); else FA_LAUNCH(128, true, false); }
     else      { if (causal) FA_LAUNCH(128, false, true); else FA_LAUNCH(128, false, false); }
@@ -308,6 +384,9 @@ int fa_b200_forward(const fa_b200_params* p) {
     else      { if (causal) FA_LAUNCH(64, false, true); else FA_LAUNCH(64, false, false); }
   }
 #undef FA_LAUNCH
+  if (rc || nsplit == 1) return rc;
+  return fa::launch_split_combine(ws_o, ws_lse, ws_m, p->O, p->lse, p->l, p->m, nsplit, rows_total, d, p->H, Nq, os.b, os.h,
+                                  os.n, ssb, ssh, p->dtype, stream);
 }
 
 int fa_b200_forward_legacy(const void* Q, const void* K, const void* V, void* O, float* l, float* m,

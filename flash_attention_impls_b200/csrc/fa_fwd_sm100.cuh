@@ -44,6 +44,10 @@ struct FwdArgs {
   int num_items;    // B*H*num_q_blocks work items (= grid size; later ones are stolen by resident CTAs)
   int num_bh;       // B*H
   int group_heads;  // causal item ordering: heads per L2-sized group (see get_item)
+  // split-KV (launches with fewer items than SMs): every (b,h,q-block) is cut into `nsplit` items that each visit
+  // `tiles_per_split` consecutive K/V tiles and write a partial (O, lse, m) for batch index split*B + b of the
+  // workspace; fa_split_combine_kernel merges them.  nsplit == 1: off.
+  int nsplit, tiles_per_split, B;
   float scale_log2; // softmax_scale * log2(e)
   long long stat_stride_b, stat_stride_h;
   int H;            // heads per batch (a work item's bh is split into (b, h) for the 4-D tensor maps)
@@ -153,6 +157,8 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, uint32_t s
 // One work item = 256 query rows of one (b,h).  Every role walks the same deterministic item list.
 struct WorkItem {
   int bh, q0, n_t0, n_t1, n_max;
+  int kv_begin;          // first K/V tile this item visits (non-zero only with split-KV)
+  int out_b;             // batch index used for the outputs (split * B + b with split-KV, else b)
   bool valid0, valid1;   // tile has at least one real query row
 };
 
@@ -160,6 +166,11 @@ template <bool kCausal>
 __host__ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
   WorkItem it;
   int qb;
+  int split = 0;
+  if (a.nsplit > 1) {       // split index is the fastest-varying part of the item id
+    split = w % a.nsplit;
+    w /= a.nsplit;
+  }
   if (kCausal) {
     // Causal items differ in length (q-block qb visits qb+1.. K/V tiles), so the list is ordered
     // longest-first, but only within groups of `group_heads` heads whose K/V fit the L2 together:
@@ -191,6 +202,18 @@ __host__ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
   };
   it.n_t0 = tiles_for(it.q0);
   it.n_t1 = tiles_for(it.q0 + kBlockM);
+  it.kv_begin = 0;
+  it.out_b = it.bh / a.H;
+  if (a.nsplit > 1) {       // restrict both tiles to this split's K/V tile range
+    it.kv_begin = split * a.tiles_per_split;
+    auto clampn = [&](int n) {
+      n -= it.kv_begin;
+      return n < 0 ? 0 : (n < a.tiles_per_split ? n : a.tiles_per_split);
+    };
+    it.n_t0 = clampn(it.n_t0);
+    it.n_t1 = clampn(it.n_t1);
+    it.out_b += split * a.B;
+  }
   it.n_max = it.n_t0 > it.n_t1 ? it.n_t0 : it.n_t1;
   it.valid0 = it.q0 < a.Nq;
   it.valid1 = it.q0 + kBlockM < a.Nq;
@@ -332,7 +355,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               const int stage = it % kStages;
               const uint32_t ph = (it / kStages) & 1;
               mbar_wait(bar_kv_empty + 8 * stage, ph ^ 1, 100 + kv);
-              load_tile(kv == 0 ? &tmK : &tmV, a.perm_kv, sKV + stage * kTileBytes, bar_kv_full + 8 * stage, j * kBlockN);
+              load_tile(kv == 0 ? &tmK : &tmV, a.perm_kv, sKV + stage * kTileBytes, bar_kv_full + 8 * stage, (wi.kv_begin + j) * kBlockN);
               ++it;
               if (j == 0 && kv == 0 && wi.n_t1 > 0) {
                 mbar_wait(bar_q_empty + 8, (nq[1] & 1u) ^ 1u, 111);
@@ -529,7 +552,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (row_in_tile == 0) {
 #pragma unroll
           for (int h = 0; h < kNumBoxes; ++h)
-            tma_store_tile(&tmO, sO + h * kBoxBytes, h * kBoxCols, wi.q0 + i * kBlockM, wi.bh % a.H, wi.bh / a.H, a.perm_o);
+            tma_store_tile(&tmO, sO + h * kBoxBytes, h * kBoxCols, wi.q0 + i * kBlockM, wi.bh % a.H, wi.out_b, a.perm_o);
           tma_store_commit();
         }
         store_pending = true;
@@ -555,12 +578,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     int w = blockIdx.x;
     for (int t = 0; w >= 0; ++t) {
       const int w_cur = w;
-      int n_i, limit;
+      int n_i, limit, kv_begin;
       bool valid;
       {
         const WorkItem wi = get_item<kCausal>(a, w_cur);
         valid = i ? wi.valid1 : wi.valid0;
         n_i = i ? wi.n_t1 : wi.n_t0;
+        kv_begin = wi.kv_begin;
         // last visible key index for this row
         limit = a.Nkv - 1;
         if (kCausal) limit = min(limit, wi.q0 + i * kBlockM + row_in_tile + a.causal_off);
@@ -586,7 +610,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 1);
 
         // masking: key index > limit -> -inf (diagonal tiles of causal runs, ragged last tile)
-        const int lim_local = limit - j * kBlockN;
+        const int lim_local = limit - (kv_begin + j) * kBlockN;
         if (__any_sync(0xffffffffu, lim_local < kBlockN - 1)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -668,7 +692,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       cnt += uint32_t(n_i);
 
       // ---- hand the row normaliser to the epilogue warpgroup, write the row statistics, move on
-      if (limit < 0) l = 0.f;   // row sees no key at all: the polynomial exp2 returns 2^-127, not 0
+      if (limit < kv_begin * kBlockN) l = 0.f;   // row sees no key of this item: the polynomial exp2 returns 2^-127, not 0
       const float inv_l = (l > 0.f) ? (1.f / l) : 0.f;
       mbar_wait(bar_ep_empty + 8 * i, (ne & 1u) ^ 1u, 330 + i);   // slot of the previous hand-off consumed
       ++ne;
@@ -677,7 +701,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const WorkItem wi = get_item<kCausal>(a, w_cur);   // recomputed here to keep it out of the hot loop's registers
       const int row = wi.q0 + i * kBlockM + row_in_tile;
       if (row < a.Nq) {
-        const long long off = (long long)(wi.bh / a.H) * a.stat_stride_b + (long long)(wi.bh % a.H) * a.stat_stride_h + row;
+        const long long off = (long long)wi.out_b * a.stat_stride_b + (long long)(wi.bh % a.H) * a.stat_stride_h + row;
         const float ln2 = 0.6931471805599453f;
         const bool any = l > 0.f;
         if (a.lse) a.lse[off] = any ? fmaf(m_ref, ln2, logf(l)) : -INFINITY;

@@ -94,12 +94,89 @@ cast_output_kernel(uint4* __restrict__ O, const float4* __restrict__ O_acc, long
   }
 }
 
+// Split-KV combine: partial (O_s, lse_s, m_s), s < nsplit, of the same rows over disjoint key ranges ->
+//   lse = log sum_s e^lse_s,  O = sum_s e^(lse_s - lse) O_s,  m = max_s m_s,  l = e^(lse - m).
+// Partials are dense [nsplit][rows][d] / [nsplit][rows]; the outputs use the caller's strides.
+// One thread per 8 consecutive elements of a row.
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+split_combine_kernel(const uint4* __restrict__ O_part, const float* __restrict__ lse_part,
+                     const float* __restrict__ m_part, char* __restrict__ O, float* __restrict__ lse,
+                     float* __restrict__ l, float* __restrict__ m, int nsplit, long long rows, int d, int H, int N,
+                     long long o_sb, long long o_sh, long long o_sn, long long st_sb, long long st_sh) {
+  const int vec_per_row = d / 8;
+  const long long total = rows * vec_per_row;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / vec_per_row;
+    const int v = (int)(idx - row * vec_per_row);
+    float mx = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) mx = fmaxf(mx, lse_part[s * rows + row]);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float sum = 0.f;
+    if (mx != -INFINITY) {
+      for (int s = 0; s < nsplit; ++s) {
+        const float ls = lse_part[s * rows + row];
+        if (ls == -INFINITY) continue;
+        const float w = __expf(ls - mx);
+        sum += w;
+        const uint4 pv = O_part[(s * rows + row) * vec_per_row + v];
+        const float2 p0 = unpack2<kBF16>(pv.x), p1 = unpack2<kBF16>(pv.y), p2 = unpack2<kBF16>(pv.z),
+                     p3 = unpack2<kBF16>(pv.w);
+        acc[0] += w * p0.x; acc[1] += w * p0.y; acc[2] += w * p1.x; acc[3] += w * p1.y;
+        acc[4] += w * p2.x; acc[5] += w * p2.y; acc[6] += w * p3.x; acc[7] += w * p3.y;
+      }
+    }
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    const long long b = row / ((long long)H * N);
+    const long long rem = row - b * (long long)H * N;
+    const long long h = rem / N, n = rem - h * N;
+    uint4 o;
+    o.x = pack2f<kBF16>(acc[0] * inv, acc[1] * inv); o.y = pack2f<kBF16>(acc[2] * inv, acc[3] * inv);
+    o.z = pack2f<kBF16>(acc[4] * inv, acc[5] * inv); o.w = pack2f<kBF16>(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(O + (b * o_sb + h * o_sh + n * o_sn + v * 8) * 2) = o;
+    if (v == 0) {
+      const long long so = b * st_sb + h * st_sh + n;
+      const float lse_v = sum > 0.f ? mx + __logf(sum) : -INFINITY;
+      if (lse) lse[so] = lse_v;
+      if (m || l) {
+        float mm = -INFINITY;
+        for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, m_part[s * rows + row]);
+        if (m) m[so] = mm;
+        if (l) l[so] = sum > 0.f ? __expf(lse_v - mm) : 0.f;
+      }
+    }
+  }
+}
+
+// launched by fa_api.cu after the split-KV forward kernel
+int launch_split_combine(const void* O_part, const float* lse_part, const float* m_part, void* O, float* lse,
+                         float* l, float* m, int nsplit, long long rows, int d, int H, int N, long long o_sb,
+                         long long o_sh, long long o_sn, long long st_sb, long long st_sh, int dtype,
+                         cudaStream_t stream);
+
 inline unsigned grid_for(long long work_items) {
   long long blocks = (work_items + 255) / 256;
   const long long cap = 148LL * 8;   // 8 resident 256-thread CTAs per SM, 148 SMs
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
+}
+int launch_split_combine(const void* O_part, const float* lse_part, const float* m_part, void* O, float* lse,
+                         float* l, float* m, int nsplit, long long rows, int d, int H, int N, long long o_sb,
+                         long long o_sh, long long o_sn, long long st_sb, long long st_sh, int dtype,
+                         cudaStream_t stream) {
+  const long long total = rows * (d / 8);
+  if (dtype == FA_B200_BF16)
+    split_combine_kernel<true><<<grid_for(total), 256, 0, stream>>>((const uint4*)O_part, lse_part, m_part, (char*)O, lse, l,
+                                                                    m, nsplit, rows, d, H, N, o_sb, o_sh, o_sn, st_sb, st_sh);
+  else
+    split_combine_kernel<false><<<grid_for(total), 256, 0, stream>>>((const uint4*)O_part, lse_part, m_part, (char*)O, lse, l,
+                                                                     m, nsplit, rows, d, H, N, o_sb, o_sh, o_sn, st_sb, st_sh);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return FA_B200_OK;
 }
 }  // namespace fa
 

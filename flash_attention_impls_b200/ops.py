@@ -42,7 +42,7 @@ def _require_cuda(*ts: torch.Tensor) -> None:
 def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool = False,
                       softmax_scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
                       lse: Optional[torch.Tensor] = None, l: Optional[torch.Tensor] = None,
-                      m: Optional[torch.Tensor] = None, return_lse: bool = True):
+                      m: Optional[torch.Tensor] = None, return_lse: bool = True, allow_split: bool = True):
     """O = softmax(Q K^T * scale [+ causal mask]) V on [B,H,N,d] tensors; returns (O, lse).
 
     q: [B,H,N,d]; k, v: [B,H,N_kv,d]; fp16 or bf16.  Only the last dim has to be contiguous: batch, head and row
@@ -104,6 +104,12 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
     p.stat_stride_b, p.stat_stride_h = ss
     p.stream = _stream_ptr(q)
     with torch.cuda.device(q.device):
+        # split-KV scratch for launches that would leave most SMs idle (torch's caching allocator owns it;
+        # the library itself never allocates)
+        ws_bytes = int(_lib.load().fa_b200_workspace_bytes(B, H, N, p.N_kv, d)) if allow_split else 0
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes else None
+        if ws is not None:
+            p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
         _lib.check(_lib.load().fa_b200_forward(ctypes.byref(p)))
     return out, lse
 

@@ -83,10 +83,19 @@ typedef struct fa_b200_params {
   int64_t o_stride_b, o_stride_h, o_stride_n;
   int64_t stat_stride_b, stat_stride_h;
   void* stream;      /* cudaStream_t; NULL => legacy default stream, as in the reference */
+  /* Optional device scratch for split-KV scheduling: launches with far fewer (b,h,256-row) work items than SMs
+   * (e.g. the reference's (1,1,N,64) sweep, report/pmph-a6.tex:282-286) are cut along the key axis into partial
+   * results that a second kernel combines with their logsumexp.  Size it with fa_b200_workspace_bytes(); NULL or
+   * too small => the plain single-pass schedule.  The callee still allocates nothing. */
+  void* workspace;
+  size_t workspace_bytes;
 } fa_b200_params;
 
 /* Primary entry point. */
 int fa_b200_forward(const fa_b200_params* p);
+
+/* Scratch bytes fa_b200_forward would like for this shape (0 when it would not split). */
+size_t fa_b200_workspace_bytes(int B, int H, int N, int N_kv, int d);
 
 /* Same argument list as the reference kernel flash_attention_forward (flashAttention.h:8-11)
  * plus the stream; call this where the reference does `flash_attention_forward<<<grid,block,

@@ -42,8 +42,8 @@ def test_reference_named_cxx_shims_are_exported():
 
 
 def test_struct_layout_matches_header():
-    # 7 pointers, 7 ints + float, 11 int64 strides, 1 pointer  (x86-64 LP64)
-    assert ctypes.sizeof(_lib.FaB200Params) == 7 * 8 + 8 * 4 + 11 * 8 + 8
+    # 7 pointers, 7 ints + float, 11 int64 strides, stream, workspace pointer + size  (x86-64 LP64)
+    assert ctypes.sizeof(_lib.FaB200Params) == 7 * 8 + 8 * 4 + 11 * 8 + 8 + 16
 
 
 def test_version_and_status_strings():
@@ -104,3 +104,15 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle." not in text and "import oracle" not in text and "liboracle" not in text, f
+
+
+def test_workspace_query_policy():
+    """Split-KV is only proposed for launches that would leave most SMs idle and are long enough to cut."""
+    lib = _lib.load()
+    assert lib.fa_b200_workspace_bytes(4, 32, 8192, 0, 128) == 0          # c3: 4096 items, no split
+    assert lib.fa_b200_workspace_bytes(8, 16, 1024, 0, 64) == 0           # c2: 512 items
+    assert lib.fa_b200_workspace_bytes(1, 1, 512, 0, 64) == 0             # too short to split
+    n = lib.fa_b200_workspace_bytes(1, 1, 8192, 0, 64)                    # the reference's (1,1,8192,64) sweep point
+    assert n > 0 and n % (8192 * (64 * 2 + 8)) == 0
+    assert 2 <= n // (8192 * (64 * 2 + 8)) <= 32
+    assert lib.fa_b200_workspace_bytes(1, 1, 8192, 0, 48) == 0            # invalid shape -> 0

@@ -41,7 +41,8 @@ def _run(fa, q, k, v, dtype, causal, stats=True):
     before = fa.launch_count()
     o, lse = fa.attention_forward(tq, tk, tv, causal=causal, l=l, m=m)
     torch.cuda.synchronize()
-    assert fa.launch_count() == before + 1           # the CUDA kernel really launched
+    # the CUDA kernel really launched (+1 combine kernel when the split-KV schedule was picked)
+    assert fa.launch_count() - before in (1, 2)
     return o.float().cpu().numpy(), lse.cpu().numpy(), (l.cpu().numpy() if stats else None), (m.cpu().numpy() if stats else None)
 
 
@@ -277,6 +278,39 @@ def test_batch_strided_views(fa):
     _check(o.float().cpu().numpy(), lse.cpu().numpy(), o_ref, lse_ref)
 
 
+@pytest.mark.parametrize("B,H,N,Nkv,d,dtype,causal", [
+    (1, 1, 8192, 8192, 64, "fp16", False),    # the reference's (1,1,N,64) sweep, report/pmph-a6.tex:282-286
+    (1, 1, 8192, 8192, 64, "fp16", True),
+    (1, 2, 4096, 4096, 128, "bf16", True),
+    (1, 1, 5000, 5000, 64, "bf16", False),    # ragged: last split shorter, last tile masked
+    (1, 3, 300, 6000, 128, "bf16", True),     # few queries, many keys (decode-like), bottom-right causal
+    (2, 1, 2500, 1200, 32, "fp16", True),     # N_kv < N: rows (and whole splits) without any key
+])
+def test_split_kv_schedule(fa, B, H, N, Nkv, d, dtype, causal):
+    """Launches with far fewer work items than SMs are cut along the key axis (fa_b200_workspace_bytes > 0) and the
+    partials combined with their logsumexp; results must match the oracle and the single-pass schedule."""
+    from flash_attention_impls_b200 import _lib
+    from oracle import oracle
+    assert _lib.load().fa_b200_workspace_bytes(B, H, N, 0 if Nkv == N else Nkv, d) > 0
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, Nkv, d), seeds=(71, 72, 73))
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, _dt(dtype)) for x in (q, k, v))
+    l = torch.empty((B, H, N), dtype=torch.float32, device=dev); m = torch.empty_like(l)
+    n0 = fa.launch_count()
+    o, lse = fa.attention_forward(tq, tk, tv, causal=causal, l=l, m=m)
+    torch.cuda.synchronize()
+    assert fa.launch_count() == n0 + 2          # forward kernel + combine kernel
+    o1, lse1 = fa.attention_forward(tq, tk, tv, causal=causal, allow_split=False)
+    torch.cuda.synchronize()
+    assert fa.launch_count() == n0 + 3
+    o_ref, lse_ref, l_ref, m_ref = oracle.attention(q, k, v, causal=causal)
+    _check(o.float().cpu().numpy(), lse.cpu().numpy(), o_ref, lse_ref)
+    fin = np.isfinite(lse_ref)
+    assert np.abs(m.cpu().numpy()[fin] - m_ref[fin]).max() <= 1e-4
+    assert (np.abs(l.cpu().numpy()[fin] - l_ref[fin]) / np.maximum(1.0, l_ref[fin])).max() <= 1e-3
+    assert (o.float() - o1.float()).abs().max().item() <= O_TOL
+
+
 def test_merge_partial_kernel(fa):
     """attention over [K1;K2] == merge(attention(K1), attention(K2)) (the ring-attention identity)."""
     from oracle import oracle
@@ -386,7 +420,8 @@ def test_full_size_c2(fa):
 def test_host_pipeline_e2e_matches_device_path(fa):
     B, H, N, d = 2, 8, 1024, 128
     q, k, v = _full_inputs(B, H, N, d, torch.bfloat16, seed=9)
-    o, lse = fa.attention_forward(q, k, v, causal=True)
+    # single-pass schedule on both sides (the host pipeline never passes split-KV scratch)
+    o, lse = fa.attention_forward(q, k, v, causal=True, allow_split=False)
     pipe = fa.HostPipeline(B, H, N, d, torch.bfloat16, causal=True, chunks=5)
     hq, hk, hv = (t.cpu().pin_memory() for t in (q, k, v))
     ho = torch.empty_like(hq).pin_memory(); hl = torch.empty((B, H, N), dtype=torch.float32).pin_memory()

@@ -113,6 +113,10 @@ static int run_attn(int argc, char** argv) {
   memset(&p, 0, sizeof(p));
   p.Q = dQ; p.K = dK; p.V = dV; p.O = dO; p.lse = dlse; p.l = dl; p.m = dm;
   p.B = B; p.H = H; p.N = N; p.d = d; p.N_kv = (Nkv == N) ? 0 : Nkv; p.dtype = dtype; p.causal = causal;
+  // split-KV scratch (only asked for when the launch would leave most SMs idle); FA_NO_SPLIT=1 disables it
+  const size_t ws_bytes = getenv("FA_NO_SPLIT") ? 0 : fa_b200_workspace_bytes(B, H, N, p.N_kv, d);
+  void* ws = nullptr;
+  if (ws_bytes) { CK(cudaMalloc(&ws, ws_bytes)); p.workspace = ws; p.workspace_bytes = ws_bytes; }
   int rc = fa_b200_forward(&p);
   if (rc) { printf("RESULT attn FAIL status=%d (%s)\n", rc, fa_b200_last_error()); return 1; }
   cudaError_t e = cudaDeviceSynchronize();
@@ -159,9 +163,9 @@ static int run_attn(int argc, char** argv) {
   const float sym = oracle_max_symmetric_rel_err(ogpu.data(), oref.data(), ogpu.size());
   const bool pass = nan_o == 0 && max_o <= 2e-3 && max_lse <= 1e-4;
   printf("RESULT attn %s B=%d H=%d N=%d Nkv=%d d=%d %s causal=%d set=%c checked_bh=%d  O_maxabs=%.3e (bad=%zu nan=%zu) "
-         "lse_rel=%.3e m_abs=%.3e l_rel=%.3e sym_rel=%.4f\n",
+         "lse_rel=%.3e m_abs=%.3e l_rel=%.3e sym_rel=%.4f%s\n",
          pass ? "PASS" : "FAIL", B, H, N, Nkv, d, bf16 ? "bf16" : "fp16", causal, set, bh_check, max_o, bad_o,
-         nan_o, max_lse, max_m, max_l, sym);
+         nan_o, max_lse, max_m, max_l, sym, ws_bytes ? " [split-KV]" : "");
   if (!pass) {
     // print a few rows to help localise the bug
     for (int r : {0, 1, 127, 128, N - 1}) {
