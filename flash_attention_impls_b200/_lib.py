@@ -24,7 +24,8 @@ STATUS = {
 EXPORTED_SYMBOLS = (
     "fa_b200_forward", "fa_b200_workspace_bytes", "fa_b200_forward_legacy", "fa_b200_forward_fp16", "fa_b200_merge_partial",
     "fa_b200_cast_output", "fa_b200_host_ctx_create", "fa_b200_forward_host", "fa_b200_host_ctx_sync",
-    "fa_b200_host_ctx_elapsed_ms", "fa_b200_host_ctx_destroy", "fa_b200_work_item", "fa_b200_launch_count", "fa_b200_last_error", "fa_b200_status_string",
+    "fa_b200_host_ctx_elapsed_ms", "fa_b200_host_ctx_destroy", "fa_b200_peer_alloc", "fa_b200_peer_free", "fa_b200_peer_open",
+    "fa_b200_peer_close", "fa_b200_copy_async", "fa_b200_work_item", "fa_b200_launch_count", "fa_b200_last_error", "fa_b200_status_string",
     "fa_b200_version",
 )
 
@@ -89,6 +90,16 @@ def load() -> ctypes.CDLL:
     lib.fa_b200_host_ctx_elapsed_ms.restype = c_int
     lib.fa_b200_host_ctx_destroy.argtypes = [c_void_p]
     lib.fa_b200_host_ctx_destroy.restype = None
+    lib.fa_b200_peer_alloc.argtypes = [ctypes.c_size_t, POINTER(c_void_p), ctypes.c_char_p]
+    lib.fa_b200_peer_alloc.restype = c_int
+    lib.fa_b200_peer_free.argtypes = [c_void_p]
+    lib.fa_b200_peer_free.restype = c_int
+    lib.fa_b200_peer_open.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
+    lib.fa_b200_peer_open.restype = c_int
+    lib.fa_b200_peer_close.argtypes = [c_void_p]
+    lib.fa_b200_peer_close.restype = c_int
+    lib.fa_b200_copy_async.argtypes = [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]
+    lib.fa_b200_copy_async.restype = c_int
     lib.fa_b200_work_item.argtypes = [c_int] * 7 + [POINTER(c_int)] * 4
     lib.fa_b200_work_item.restype = c_int
     lib.fa_b200_launch_count.argtypes = []

@@ -162,3 +162,46 @@ extern "C" void fa_b200_host_ctx_destroy(fa_b200_host_ctx* c) {
   if (c->ev_last) cudaEventDestroy(c->ev_last);
   delete c;
 }
+
+// ---------------------------------------------------------------------------------------------- peer memory
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+extern "C" int fa_b200_peer_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]) {
+  if (!dev_ptr || !handle || bytes == 0) return fa::api_fail(FA_B200_ERR_NULL, "peer_alloc: bad argument");
+  int rc = fa::api_check_device();
+  if (rc) return rc;
+  FA_TRY(cudaMalloc(dev_ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*dev_ptr);
+    *dev_ptr = nullptr;
+    return fa::api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
+  }
+  memcpy(handle, &h, 64);
+  return FA_B200_OK;
+}
+
+extern "C" int fa_b200_peer_free(void* dev_ptr) {
+  if (dev_ptr) FA_TRY(cudaFree(dev_ptr));
+  return FA_B200_OK;
+}
+
+extern "C" int fa_b200_peer_open(const unsigned char handle[64], void** dev_ptr) {
+  if (!dev_ptr || !handle) return fa::api_fail(FA_B200_ERR_NULL, "peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  FA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FA_B200_OK;
+}
+
+extern "C" int fa_b200_peer_close(void* dev_ptr) {
+  if (dev_ptr) FA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return FA_B200_OK;
+}
+
+extern "C" int fa_b200_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return fa::api_fail(FA_B200_ERR_NULL, "copy_async: NULL pointer");
+  FA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream)));
+  return FA_B200_OK;
+}

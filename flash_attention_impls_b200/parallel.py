@@ -3,10 +3,12 @@ multi-GPU code at all; both modes are new work named by BASELINE.json's north_st
 
 * (batch, head) sharding — `[B,H,N,d]` is contiguous in b*H+h (reference: flashAttention.cu:30), the
   (b,h) slices are independent, so rank g of P simply owns a contiguous range of them.  No collective.
-* ring attention — the sequence is split over the ranks; K/V blocks travel with NCCL send/recv
-  (torch.distributed P2P over NVLink/NVSwitch) while each rank runs the local kernel on the block it holds,
-  in ring order (step s uses the block of rank r-s), and the per-block partials are merged with their
-  logsumexp.  Causal runs use the zig-zag partition (rank r owns
+* ring attention — the sequence is split over the ranks; each rank runs the local kernel on one K/V block
+  at a time, in ring order (step s uses the block of rank r-s), and the per-block partials are merged with
+  their logsumexp.  The blocks travel over NVLink/NVSwitch in one of two ways: `transport="peer"` (default on a
+  single node): every rank publishes its block in a CUDA-IPC buffer and the others PULL it with the copy
+  engines, which needs no SM; `transport="p2p"`: NCCL send/recv through torch.distributed (also what the CPU/gloo
+  tests of the schedule use).  Causal runs use the zig-zag partition (rank r owns
   sequence chunks r and 2P-1-r) so that every rank does the same amount of work at every step.
 
 One process per GPU; the compute calls go to libfa_b200.so through `ops`.  The `backend` argument
@@ -15,6 +17,7 @@ exists so the schedule/partition logic can be tested with gloo on CPU against th
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -71,6 +74,26 @@ class _CudaBackend:
         return ops.cast_output(o_acc, dtype)
 
 
+class _RingProfile:
+    """FA_B200_RING_PROFILE=1: CUDA-event timeline of one ring_attention call (diagnostics only)."""
+
+    def __init__(self, device):
+        self.marks = []
+        self.device = device
+        self.mark("start")
+
+    def mark(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.marks.append((name, ev))
+
+    def report(self, rank):
+        torch.cuda.synchronize(self.device)
+        t0 = self.marks[0][1]
+        line = " ".join(f"{n}={t0.elapsed_time(e):.2f}" for n, e in self.marks[1:])
+        print(f"[ring profile rank {rank}] ms since start: {line}", flush=True)
+
+
 def _post_block_exchange(k, v, recv_k, recv_v, step, group, rank, world):
     """Post the transfers of ring step `step`: my own K/V block goes to the rank that needs it at that step,
     (rank + step) mod P, and the block I need, the one owned by (rank - step) mod P, comes in.
@@ -91,8 +114,84 @@ def _post_block_exchange(k, v, recv_k, recv_v, step, group, rank, world):
     return dist.batch_isend_irecv(ops_)
 
 
+class _PeerRing:
+    """K/V exchange over peer memory: CUDA-IPC buffers + copy-engine pulls (see include/fa_b200.h, peer section).
+
+    One instance per (block bytes, group, device), cached in `_peer_rings`.  Each rank owns two publish buffers
+    (K|V, double-buffered across calls) that every other rank of the node has mapped.  A call writes the local block
+    into publish buffer `n % 2`, runs one tiny all-reduce as the cross-rank "everything is published" barrier, then
+    pulls the P-1 remote blocks on a side stream, one event per block.  Because call n+1 uses the other buffer and
+    its barrier is stream-ordered after call n's compute, a buffer is only overwritten two calls later, when every
+    peer has finished pulling from it."""
+
+    def __init__(self, block_bytes: int, group, device):
+        import ctypes
+        from . import _lib
+        self.lib, self.ct = _lib, ctypes
+        self.group, self.device, self.block_bytes = group, device, block_bytes
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.calls = 0
+        self.mine, handles = [], []
+        with torch.cuda.device(device):
+            for _ in range(2):
+                ptr = ctypes.c_void_p()
+                h = ctypes.create_string_buffer(64)
+                _lib.check(_lib.load().fa_b200_peer_alloc(2 * block_bytes, ctypes.byref(ptr), h))
+                self.mine.append(ptr.value)
+                handles.append(h.raw)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, handles, group=group)
+            self.peers = []            # peers[r][buf] -> device pointer of rank r's publish buffer
+            for r, hs in enumerate(gathered):
+                if r == self.rank:
+                    self.peers.append(list(self.mine))
+                    continue
+                ptrs = []
+                for raw in hs:
+                    p_ = ctypes.c_void_p()
+                    _lib.check(_lib.load().fa_b200_peer_open(raw, ctypes.byref(p_)))
+                    ptrs.append(p_.value)
+                self.peers.append(ptrs)
+            self.copy_stream = torch.cuda.Stream(device)
+            self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def exchange(self, k, v, blocks):
+        """Publishes (k, v), then starts pulling blocks[s] <- rank (r - s) mod P for s = 1..P-1.
+        Returns one CUDA event per step (None for step 0)."""
+        lib, buf = self.lib.load(), self.calls % 2
+        self.calls += 1
+        cur = torch.cuda.current_stream(self.device)
+        nb = self.block_bytes
+        with torch.cuda.device(self.device):
+            self.lib.check(lib.fa_b200_copy_async(self.mine[buf], k.data_ptr(), nb, cur.cuda_stream))
+            self.lib.check(lib.fa_b200_copy_async(self.mine[buf] + nb, v.data_ptr(), nb, cur.cuda_stream))
+            dist.all_reduce(self.flag, group=self.group)          # every rank's block is published
+            self.copy_stream.wait_stream(cur)
+            events = [None]
+            for s in range(1, self.world):
+                src = self.peers[(self.rank - s) % self.world][buf]
+                bk, bv = blocks[s]
+                self.lib.check(lib.fa_b200_copy_async(bk.data_ptr(), src, nb, self.copy_stream.cuda_stream))
+                self.lib.check(lib.fa_b200_copy_async(bv.data_ptr(), src + nb, nb, self.copy_stream.cuda_stream))
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                events.append(ev)
+        return events
+
+
+_peer_rings = {}
+
+
+def _peer_ring_for(k, group):
+    key = (k.numel() * k.element_size(), id(group), k.device.index)
+    ring = _peer_rings.get(key)
+    if ring is None:
+        ring = _peer_rings[key] = _PeerRing(key[0], group, k.device)
+    return ring
+
+
 def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False,
-                   group: Optional[dist.ProcessGroup] = None, backend=None):
+                   group: Optional[dist.ProcessGroup] = None, backend=None, transport: str = "auto"):
     """Ring attention over the ranks of `group`.
 
     q, k, v: this rank's shard `[B, H, N_local, d]` of a sequence of length `P * N_local`.
@@ -100,9 +199,11 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
       causal:     the zig-zag partition (`zigzag_split`): local rows = [chunk r ; chunk 2P-1-r].
     Returns (O_local `[B,H,N_local,d]` in q.dtype, lse_local `[B,H,N_local]` fp32).
 
-    Step s (s = 0..P-1) works on the block owned by rank (r - s) mod P; the P-1 remote blocks are fetched
-    with NCCL send/recv posted up front (see _post_block_exchange), so step s never waits on step s-1's
-    transfer.  With the zig-zag layout the causal structure per step is one of
+    Step s (s = 0..P-1) works on the block owned by rank (r - s) mod P; all P-1 remote blocks are requested up
+    front, so step s never waits on step s-1's transfer.  transport: "peer" = copy-engine pulls from CUDA-IPC
+    buffers (single node, no SM used), "p2p" = torch.distributed send/recv (NCCL or gloo), "auto" = "peer" for
+    CUDA tensors with the built-in backend, else "p2p".  With the zig-zag layout the causal structure per step
+    is one of
       src == r : square causal on the local block
       src <  r : every local query row sees only the FIRST half of the visiting block (no mask)
       src >  r : only the SECOND half of the local query rows see the visiting block (no mask)
@@ -125,14 +226,30 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
 
     own_k, own_v = k.contiguous(), v.contiguous()
     blocks = [(own_k, own_v)] + [(torch.empty_like(own_k), torch.empty_like(own_v)) for _ in range(world - 1)]
-    reqs = [None] + [_post_block_exchange(own_k, own_v, blocks[s][0], blocks[s][1], s, group, rank, world)
-                     for s in range(1, world)]
+    if transport == "auto":
+        transport = "peer" if (backend is None and q.is_cuda and world > 1) else "p2p"
+    if transport not in ("peer", "p2p"):
+        raise ValueError("transport must be 'auto', 'peer' or 'p2p'")
+    reqs, events = None, None
+    if world > 1 and transport == "peer":
+        events = _peer_ring_for(own_k, group).exchange(own_k, own_v, blocks)
+    elif world > 1:
+        reqs = [None] + [_post_block_exchange(own_k, own_v, blocks[s][0], blocks[s][1], s, group, rank, world)
+                         for s in range(1, world)]
 
+    prof = _RingProfile(q.device) if os.environ.get("FA_B200_RING_PROFILE") else None
     for step in range(world):
         src = (rank - step) % world
+        if prof:
+            prof.mark(f"s{step}:begin")
         if step > 0:
-            for r_ in reqs[step]:
-                r_.wait()
+            if events is not None:
+                torch.cuda.current_stream(q.device).wait_event(events[step])
+            else:
+                for r_ in reqs[step]:
+                    r_.wait()
+        if prof:
+            prof.mark(f"s{step}:kv_ready")
         cur_k, cur_v = blocks[step]
 
         if not causal or src == rank:
@@ -144,6 +261,14 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
             # only the second half of the local queries (chunk 2P-1-r) sees the visiting block
             lse_part[:, :, :half].fill_(float("-inf"))
             be.attention(q[:, :, half:], cur_k, cur_v, False, o_part[:, :, half:], lse_part[:, :, half:])
+        if prof:
+            prof.mark(f"s{step}:attn_done")
         be.merge(o_acc, lse_acc, o_part, lse_part)
+        if prof:
+            prof.mark(f"s{step}:merge_done")
 
-    return be.finalize(o_acc, q.dtype), lse_acc
+    out = be.finalize(o_acc, q.dtype)
+    if prof:
+        prof.mark("finalize_done")
+        prof.report(rank)
+    return out, lse_acc

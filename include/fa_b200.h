@@ -138,6 +138,19 @@ int fa_b200_host_ctx_sync(fa_b200_host_ctx* ctx);
 int fa_b200_host_ctx_elapsed_ms(fa_b200_host_ctx* ctx, float* ms);
 void fa_b200_host_ctx_destroy(fa_b200_host_ctx* ctx);
 
+/* ---- peer memory over NVLink (ring attention transport) ----------------------------------------------------
+ * One process per GPU: a rank publishes its K/V block in a buffer it exports with CUDA IPC; the other ranks of
+ * the node map it and PULL the block with the copy engines (cudaMemcpyAsync over NVLink/NVSwitch), which needs no
+ * SM - the attention kernel occupies every SM with a persistent CTA, so SM-based send/recv kernels would only run
+ * in the gaps between launches.  fa_b200_peer_alloc: cudaMalloc + export (handle is 64 opaque bytes);
+ * fa_b200_peer_open: map a peer's buffer (peer access is enabled lazily); fa_b200_copy_async: DMA copy on
+ * `stream` between any two device pointers. */
+int fa_b200_peer_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]);
+int fa_b200_peer_free(void* dev_ptr);
+int fa_b200_peer_open(const unsigned char handle[64], void** dev_ptr);
+int fa_b200_peer_close(void* dev_ptr);
+int fa_b200_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+
 /* Introspection of the tile scheduler (host-only, no GPU needed): decodes work item `index` of the launch that
  * fa_b200_forward would make for this shape - which (b*H+h) slice, first query row, and how many 128-key K/V
  * tiles each of its two 128-row Q tiles visits (0 = tile skipped).  Returns the number of work items

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, causal, N, d, q_out):
+def _worker(rank, world, port, causal, N, d, q_out, transport="auto"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -30,25 +30,26 @@ def _worker(rank, world, port, causal, N, d, q_out):
         else:
             c = N // world
             ql, kl, vl = (t[:, :, rank * c:(rank + 1) * c].contiguous() for t in (q, k, v))
-        o, lse = fa.ring_attention(ql, kl, vl, causal=causal)
+        for _ in range(3):      # repeated calls exercise the double-buffered publish slots of the peer transport
+            o, lse = fa.ring_attention(ql, kl, vl, causal=causal, transport=transport)
         torch.cuda.synchronize()
         q_out.put((rank, o.float().cpu().numpy(), lse.cpu().numpy()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("causal", [False, True])
-def test_ring_attention_nccl(causal):
+@pytest.mark.parametrize("causal,transport", [(False, "peer"), (True, "peer"), (True, "p2p")])
+def test_ring_attention_nccl(causal, transport):
     from flash_attention_impls_b200.parallel import zigzag_gather
     from oracle import oracle
     world = min(torch.cuda.device_count(), 4)
     if world < 1:
         pytest.skip("no GPU")
     N, d = 512 * world, 128
-    port = 29800 + (os.getpid() % 1000) + (5 if causal else 0)
+    port = 29800 + (os.getpid() % 1000) + (5 if causal else 0) + (11 if transport == "p2p" else 0)
     ctx = mp.get_context("spawn")
     q_out = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, causal, N, d, q_out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, causal, N, d, q_out, transport)) for r in range(world)]
     for p in procs:
         p.start()
     results = sorted((q_out.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
