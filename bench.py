@@ -8,7 +8,8 @@ One "step" = one attention forward over the whole workload.  Default workload is
 configs[2] ("c3"): B=4 H=32 N=8192 d=128 bf16 non-causal, the configuration the metric is quoted on.
 Each rank runs that workload on its own GPU ((batch,head) units are independent: no collective), so
 N-GPU runs are weak scaling and `value` is the aggregate TFLOP/s over all ranks.  With --workload c5
-the ranks cooperate on ONE sequence with ring attention (NCCL send/recv), which is strong scaling.
+the ranks cooperate on ONE sequence with ring attention (K/V blocks pulled from peer memory over NVLink,
+or NCCL send/recv with --ring-transport p2p), which is strong scaling.
 
 Prints ONE JSON line on rank 0.
 """
@@ -176,6 +177,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer arm (0 = min(steps, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ring-transport", default="auto", choices=["auto", "peer", "p2p"],
+                    help="c5 only: K/V block transport (auto = CUDA-IPC peer buffers + copy-engine pulls)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -221,7 +224,7 @@ def main():
 
     if ring:
         def step():
-            return fa.ring_attention(q, k, v, causal=causal)
+            return fa.ring_attention(q, k, v, causal=causal, transport=args.ring_transport)
         step_flops_total = flops_of(B, H, N, d, causal)          # one sequence shared by all ranks
         scaling = "strong"
     else:
@@ -341,7 +344,9 @@ def main():
             "dtype": dtype_name, "data": "synthetic",
             "config": {"workload": args.workload, "B": B, "H": H, "N": N, "d": d, "causal": causal,
                        "layout": "[B,H,N,d] contiguous", "per_gpu_tflops": value / world,
-                       "parallelism": ("ring%d (zig-zag, NCCL send/recv)" % world) if ring else
+                       "parallelism": ("ring%d (zig-zag; K/V blocks %s; lse merge)" % (
+                           world, "over NCCL send/recv" if args.ring_transport == "p2p" else
+                           "pulled from peer memory by the copy engines")) if ring else
                                       ("independent (b,h) units, %d rank(s), no collective" % world),
                        "l2": ("inputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e6))
                              if flush is None else "L2 flushed (512 MB write) between timed iterations"},
