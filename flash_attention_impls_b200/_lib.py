@@ -43,6 +43,7 @@ class FaB200Params(Structure):
         ("stat_stride_b", c_int64), ("stat_stride_h", c_int64),
         ("stream", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("precise", c_int),
     ]
 
 

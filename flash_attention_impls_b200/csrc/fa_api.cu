@@ -118,10 +118,10 @@ int check_device() {
 }
 
 
-template <int D, bool kBF16, bool kCausal>
+template <int D, bool kBF16, bool kCausal, bool kPrecise>
 int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
            const fa::FwdArgs& args, long long grid, cudaStream_t stream) {
-  auto kern = fa::fa_fwd_sm100_kernel<D, kBF16, kCausal>;
+  auto kern = fa::fa_fwd_sm100_kernel<D, kBF16, kCausal, kPrecise>;
   constexpr int smem = fa::FwdTraits<D>::kSmemBytes;
   // opt-in to > 48 KB dynamic shared memory: once per device per instantiation
   static std::atomic<unsigned long long> configured{0};
@@ -372,7 +372,10 @@ int fa_b200_forward(const fa_b200_params* p) {
   const long long grid = a.num_items;
   const bool bf16 = p->dtype == FA_B200_BF16;
   const bool causal = p->causal != 0;
-#define FA_LAUNCH(D_, BF_, C_) rc = launch<D_, BF_, C_>(tq, tk, tv, to, a, grid, stream)
+  const bool precise = p->precise != 0;
+#define FA_LAUNCH(D_, BF_, C_)                                                             \
+  rc = precise ? launch<D_, BF_, C_, true>(tq, tk, tv, to, a, grid, stream)                \
+               : launch<D_, BF_, C_, false>(tq, tk, tv, to, a, grid, stream)
   if (d == 128) {
     if (bf16) { if (causal) FA_LAUNCH(128, true, true); else FA_LAUNCH(128, true, false); }
     else      { if (causal) FA_LAUNCH(128, false, true); else FA_LAUNCH(128, false, false); }
@@ -398,6 +401,9 @@ int fa_b200_forward_legacy(const void* Q, const void* K, const void* V, void* O,
   p.B = B; p.H = H; p.N = N; p.d = d;
   p.dtype = FA_B200_FP16;
   p.stream = stream;
+  // the reference's FA1 kernel keeps P in fp32 (flashAttention.cu:107-135) and its driver gates on a relative
+  // metric (main.cu:346): match that accuracy (see fa_b200_params.precise)
+  p.precise = 1;
   return fa_b200_forward(&p);
 }
 

@@ -113,6 +113,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float2 v) { return pack2<kBF16>(v.x, v.y); }
 
+template <bool kBF16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if constexpr (kBF16) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  } else {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+}
+
 // 2^x for a pair of inputs on the FMA/ALU pipes (no MUFU): Cody-Waite split x = floor(x) + f,
 // degree-4 minimax polynomial for 2^f on [0,1) (max relative error 3e-6 with p(0) = 1 exactly; fitted by
 // linear programming on the relative error), floor(x) added straight into the exponent
@@ -220,7 +229,14 @@ __host__ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
   return it;
 }
 
-template <int D, bool kBF16, bool kCausal>
+// kPrecise: P goes to the PV MMA as TWO 16-bit operands, P = P_hi + P_lo (P_lo = the rounding residual of P_hi,
+// written to the upper 64 columns of the S tile, which are free once S is in registers), and O += P_hi V + P_lo V.
+// That gives P fp32-like accuracy, i.e. the accuracy of the reference's CUDA-core FA1 kernel, which keeps P in
+// fp32 (flashAttention.cu:107-135); with Q = K = V ~ N(0, 0.02) (the reference's own test inputs, main.cu:43-61)
+// the 2^-12 rounding of a single fp16 P shows up as up to 3 % in the reference's symmetric-relative metric on
+// outputs of magnitude 5e-6 (absolute error 6e-7), above its 2 % gate (main.cu:346).  Costs 1.5x the MMAs and four
+// more instructions per score pair; used by fa_b200_forward_legacy and on request (fa_b200_params.precise).
+template <int D, bool kBF16, bool kCausal, bool kPrecise = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -409,6 +425,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int k = 4 * h; k < 4 * h + 4; ++k)
               umma_ts(d_tmem, p_tmem + k * 8, b_lo + k * (16 * kRowBytes / 16), hi_v, idesc_pv, (acc || k > 0) ? 1u : 0u);
+            if constexpr (kPrecise) {   // O += P_lo V_j: the rounding residual of P, 64 columns further up
+#pragma unroll
+              for (int k = 4 * h; k < 4 * h + 4; ++k)
+                umma_ts(d_tmem, p_tmem + kBlockN / 2 + k * 8, b_lo + k * (16 * kRowBytes / 16), hi_v, idesc_pv, 1u);
+            }
             if (h == 1) {
               umma_commit(bar_done);
               if (bar_release) umma_commit(bar_release);
@@ -664,6 +685,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t pk[16];
+          [[maybe_unused]] uint32_t pl[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[q][2 * k]), __uint_as_float(sr[q][2 * k + 1])),
@@ -677,8 +699,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             lsum2[k & 3] = __fadd2_rn(lsum2[k & 3], pv);
             pk[k] = pack2<kBF16>(pv);
+            if constexpr (kPrecise) {
+              const float2 hi = unpack2<kBF16>(pk[k]);
+              pl[k] = pack2<kBF16>(__fadd2_rn(pv, make_float2(-hi.x, -hi.y)));
+            }
           }
           tmem_st16(tS + q * 16, pk);   // P(16-bit) over the first 64 columns of S
+          if constexpr (kPrecise) tmem_st16(tS + kBlockN / 2 + q * 16, pl);   // P_lo over columns 64..127
           if (q & 1) {
             tmem_wait_st();
             tc_fence_before();

@@ -42,13 +42,16 @@ def _require_cuda(*ts: torch.Tensor) -> None:
 def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool = False,
                       softmax_scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
                       lse: Optional[torch.Tensor] = None, l: Optional[torch.Tensor] = None,
-                      m: Optional[torch.Tensor] = None, return_lse: bool = True, allow_split: bool = True):
+                      m: Optional[torch.Tensor] = None, return_lse: bool = True, allow_split: bool = True,
+                      precise: bool = False):
     """O = softmax(Q K^T * scale [+ causal mask]) V on [B,H,N,d] tensors; returns (O, lse).
 
     q: [B,H,N,d]; k, v: [B,H,N_kv,d]; fp16 or bf16.  Only the last dim has to be contiguous: batch, head and row
     strides are passed to the kernel's TMA descriptors as they are (multiples of 8 elements), so row sub-ranges of
     a longer sequence (what the ring driver passes) and `x.transpose(1, 2)` views of [B,N,H,d] tensors need no copy.
-    k and v must share their strides.
+    k and v must share their strides.  precise=True feeds P to the tensor cores as a hi+lo pair of 16-bit operands
+    (fp32-like P, the accuracy of the reference's CUDA-core FA1 kernel; about 1.4x the time) - see
+    `fa_b200_params.precise` in include/fa_b200.h.
     """
     _require_cuda(q, k, v)
     if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
@@ -103,6 +106,7 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
     p.o_stride_b, p.o_stride_h, p.o_stride_n = os_
     p.stat_stride_b, p.stat_stride_h = ss
     p.stream = _stream_ptr(q)
+    p.precise = 1 if precise else 0
     with torch.cuda.device(q.device):
         # split-KV scratch for launches that would leave most SMs idle (torch's caching allocator owns it;
         # the library itself never allocates)

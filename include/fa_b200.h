@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define FA_B200_VERSION_MAJOR 0
-#define FA_B200_VERSION_MINOR 2
+#define FA_B200_VERSION_MINOR 3
 
 /* status codes (0 = ok).  The reference returns void and prints to stderr
  * (flash_attn_cutlass.cu:540-542, :510-514); the C ABI returns codes instead. */
@@ -89,6 +89,13 @@ typedef struct fa_b200_params {
    * too small => the plain single-pass schedule.  The callee still allocates nothing. */
   void* workspace;
   size_t workspace_bytes;
+  /* 1: feed P to the P.V tensor-core product as two 16-bit operands (P = P_hi + P_lo, the rounding residual),
+   * which gives P fp32-like accuracy - what the reference's CUDA-core FA1 kernel has (flashAttention.cu:107-135) -
+   * at about 1.4x the time.  0 (default): one 16-bit P, the usual tensor-core FlashAttention accuracy (well inside
+   * the 2e-3 max-abs gate; differs from an fp32-P result by ~2^-12 relative per product term).
+   * fa_b200_forward_legacy sets it, so that the reference's own driver keeps passing its 2 % relative gate
+   * (main.cu:346) on its near-zero test outputs. */
+  int precise;
 } fa_b200_params;
 
 /* Primary entry point. */

@@ -43,12 +43,12 @@ def test_reference_named_cxx_shims_are_exported():
 
 def test_struct_layout_matches_header():
     # 7 pointers, 7 ints + float, 11 int64 strides, stream, workspace pointer + size  (x86-64 LP64)
-    assert ctypes.sizeof(_lib.FaB200Params) == 7 * 8 + 8 * 4 + 11 * 8 + 8 + 16
+    assert ctypes.sizeof(_lib.FaB200Params) == 7 * 8 + 8 * 4 + 11 * 8 + 8 + 16 + 8   # ... + precise (int, padded)
 
 
 def test_version_and_status_strings():
     lib = _lib.load()
-    assert lib.fa_b200_version() == (0 << 16) | 2
+    assert lib.fa_b200_version() == (0 << 16) | 3
     assert lib.fa_b200_status_string(0) == b"ok"
     assert lib.fa_b200_status_string(3) == b"unsupported head_dim"
     assert lib.fa_b200_status_string(99) == b"unknown status"

@@ -125,6 +125,46 @@ def test_reference_input_distribution_set_r(fa):
     assert (np.abs(o - o_ref)[big] / (np.abs(o)[big] + np.abs(o_ref)[big] + 1e-5)).max() < 0.02
 
 
+@pytest.mark.parametrize("B,H,N,d", [(1, 8, 512, 64), (2, 4, 1024, 64), (1, 2, 2048, 128), (1, 4, 640, 32)])
+def test_legacy_entry_passes_the_reference_drivers_own_gate(fa, B, H, N, d):
+    """cuda_fa1/main.cu verifies flash_attention_forward against its naive fp32 kernel with
+    max |a-b| / (|a|+|b|+1e-5) < 2 % over ALL outputs (main.cu:319-347), on Q == K == V ~ N(0,0.02) in fp16.  Those
+    outputs reach down to 1e-6, where the 2^-12 rounding of a single fp16 P is a 2-3 % effect; the legacy entry
+    (fa_b200_forward_legacy) therefore feeds P as a hi+lo pair (fa_b200_params.precise) and must pass the gate as is."""
+    from oracle import oracle
+    q, _, _ = oracle.set_r((B, H, N, d))
+    q = q.astype(np.float16).astype(np.float32)
+    dev = torch.device("cuda:0")
+    tq = torch.from_numpy(q).to(dev, torch.float16)
+    O = torch.empty_like(tq); l = torch.empty((B, H, N), dtype=torch.float32, device=dev); m = torch.empty_like(l)
+    fa.flash_attention_forward(tq, tq, tq, O, l, m, B, H, N, d, 16384)
+    torch.cuda.synchronize()
+    o_ref, lse_ref, _, _ = oracle.attention(q, q, q)
+    o = O.float().cpu().numpy()
+    assert (np.abs(o - o_ref) / (np.abs(o) + np.abs(o_ref) + 1e-5)).max() < 0.02
+    _check(o, (m + torch.log(l)).cpu().numpy(), o_ref, lse_ref)
+
+
+@pytest.mark.parametrize("B,H,N,Nkv,d,dtype,causal", [
+    (1, 2, 1000, 1000, 128, "bf16", True), (2, 3, 777, 777, 64, "fp16", False), (1, 2, 300, 900, 32, "bf16", True),
+    (1, 1, 4096, 4096, 64, "bf16", False),          # split-KV schedule + precise
+])
+def test_precise_p_mode_matches_oracle_and_is_no_less_accurate(fa, B, H, N, Nkv, d, dtype, causal):
+    from oracle import oracle
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, Nkv, d))
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, _dt(dtype)) for x in (q, k, v))
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v, causal=causal)
+    o0, lse0 = fa.attention_forward(tq, tk, tv, causal=causal)
+    o1, lse1 = fa.attention_forward(tq, tk, tv, causal=causal, precise=True)
+    torch.cuda.synchronize()
+    _check(o1.float().cpu().numpy(), lse1.cpu().numpy(), o_ref, lse_ref)
+    assert torch.equal(lse0, lse1)            # the statistics do not depend on how P is fed to the tensor cores
+    e0 = np.abs(o0.float().cpu().numpy() - o_ref).mean()
+    e1 = np.abs(o1.float().cpu().numpy() - o_ref).mean()
+    assert e1 <= e0 * 1.02 + 1e-9
+
+
 def test_large_score_range_exercises_lazy_rescale(fa):
     """Row maxima that keep growing along the key axis force the lazy O/l rescale path many times."""
     from oracle import oracle
@@ -198,7 +238,10 @@ def test_reference_surface_entry_points(fa):
     O3 = torch.empty_like(tq)
     fa.flash_attention_cutlass_dispatch(tq, tk, tv, O3, B, H, N, d)
     torch.cuda.synchronize()
-    assert torch.equal(o1, O2) and torch.equal(o1, O3)
+    assert torch.equal(o1, O3)
+    # the legacy entry runs the hi+lo P mode (fp32-like P, as the reference's FA1 kernel): same result within rounding
+    assert (o1.float() - O2.float()).abs().max().item() <= 2e-3
+    assert np.abs(O2.float().cpu().numpy() - o_ref).max() <= np.abs(o1.float().cpu().numpy() - o_ref).max() + 1e-6
     assert np.abs(o1.float().cpu().numpy() - o_ref).max() <= O_TOL
     assert np.abs((m + torch.log(l)).cpu().numpy() - lse_ref).max() <= 1e-4
     # fp32 inputs are down-cast to fp16 and the result cast back, as in the reference (FA2-triton.py:242-244)
