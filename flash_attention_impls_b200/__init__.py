@@ -9,6 +9,7 @@ from .ops import (  # noqa: F401
     attention_forward,
     attention_reference_dispatch,
     cast_output,
+    combine_partials,
     flash_attention,
     flash_attention_cutlass_dispatch,
     flash_attention_forward,
@@ -27,6 +28,6 @@ from .parallel import (  # noqa: F401
 __all__ = [
     "attention_forward", "flash_attention", "flash_attention_with_stats", "flash_attention_forward",
     "flash_attention_cutlass_dispatch", "flash_attention_forward_dispatch",
-    "flash_attention_small_tile_dispatch", "attention_reference_dispatch", "merge_partial", "cast_output", "HostPipeline",
+    "flash_attention_small_tile_dispatch", "attention_reference_dispatch", "merge_partial", "combine_partials", "cast_output", "HostPipeline",
     "ring_attention", "zigzag_split", "zigzag_gather", "bh_shard_range", "launch_count", "load",
 ]

@@ -202,6 +202,21 @@ extern "C" int fa_b200_merge_partial(float* O_acc, float* lse_acc, const void* O
   return FA_B200_OK;
 }
 
+extern "C" int fa_b200_combine_partials(const void* O_parts, const float* lse_parts, int nparts, void* O, float* lse,
+                                        int64_t rows, int d, int dtype, void* stream) {
+  if (!O_parts || !lse_parts || !O) return fa::api_fail(FA_B200_ERR_NULL, "combine: NULL pointer");
+  if (nparts <= 0 || rows <= 0 || rows > 0x7fffffffLL || d <= 0 || d % 8)
+    return fa::api_fail(FA_B200_ERR_SHAPE, "combine: nparts > 0, 0 < rows < 2^31 and d % 8 == 0 required");
+  if (dtype != FA_B200_FP16 && dtype != FA_B200_BF16) return fa::api_fail(FA_B200_ERR_DTYPE, "combine: bad dtype");
+  if ((reinterpret_cast<uintptr_t>(O_parts) | reinterpret_cast<uintptr_t>(O)) & 15)
+    return fa::api_fail(FA_B200_ERR_ALIGNMENT, "combine: O_parts and O must be 16-byte aligned");
+  int rc = fa::api_check_device();
+  if (rc) return rc;
+  // one "batch", one "head" of `rows` rows: dense [rows, d] output, dense [rows] statistics
+  return fa::launch_split_combine(O_parts, lse_parts, nullptr, O, lse, nullptr, nullptr, nparts, rows, d, 1, (int)rows,
+                                  0, 0, d, 0, 0, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int fa_b200_cast_output(void* O, const float* O_acc, int64_t rows, int d, int dtype, void* stream) {
   if (!O || !O_acc) return fa::api_fail(FA_B200_ERR_NULL, "cast: NULL pointer");
   if (rows <= 0 || d <= 0 || d % 8) return fa::api_fail(FA_B200_ERR_SHAPE, "cast: rows > 0 and d % 8 == 0 required");

@@ -182,6 +182,27 @@ def merge_partial(o_acc: torch.Tensor, lse_acc: torch.Tensor, o_part: torch.Tens
                                                      _stream_ptr(o_acc)))
 
 
+def combine_partials(o_parts: torch.Tensor, lse_parts: torch.Tensor, out: Optional[torch.Tensor] = None,
+                     lse: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One-pass logsumexp merge of `o_parts` [P, ..., d] (fp16/bf16) with `lse_parts` [P, ...] (fp32) over the
+    leading axis -> (O [..., d] in o_parts.dtype, lse [...] fp32).  Rows of a partial with lse = -inf are skipped."""
+    _require_cuda(o_parts, lse_parts)
+    assert o_parts.is_contiguous() and lse_parts.is_contiguous() and lse_parts.dtype == torch.float32
+    P, d = o_parts.shape[0], o_parts.shape[-1]
+    rows = o_parts[0].numel() // d
+    assert lse_parts.shape[0] == P and lse_parts[0].numel() == rows
+    if out is None:
+        out = torch.empty(o_parts.shape[1:], dtype=o_parts.dtype, device=o_parts.device)
+    if lse is None:
+        lse = torch.empty(lse_parts.shape[1:], dtype=torch.float32, device=o_parts.device)
+    assert out.is_contiguous() and lse.is_contiguous() and out.dtype == o_parts.dtype
+    with torch.cuda.device(o_parts.device):
+        _lib.check(_lib.load().fa_b200_combine_partials(o_parts.data_ptr(), lse_parts.data_ptr(), P, out.data_ptr(),
+                                                        lse.data_ptr(), rows, d, _dtype_code(o_parts),
+                                                        _stream_ptr(o_parts)))
+    return out, lse
+
+
 def cast_output(o_acc: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     _require_cuda(o_acc)
     out = torch.empty(o_acc.shape, dtype=dtype, device=o_acc.device)

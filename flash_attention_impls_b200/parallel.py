@@ -4,8 +4,9 @@ multi-GPU code at all; both modes are new work named by BASELINE.json's north_st
 * (batch, head) sharding — `[B,H,N,d]` is contiguous in b*H+h (reference: flashAttention.cu:30), the
   (b,h) slices are independent, so rank g of P simply owns a contiguous range of them.  No collective.
 * ring attention — the sequence is split over the ranks; each rank runs the local kernel on one K/V block
-  at a time, in ring order (step s uses the block of rank r-s), and the per-block partials are merged with
-  their logsumexp.  The blocks travel over NVLink/NVSwitch in one of two ways: `transport="peer"` (default on a
+  at a time, in ring order (step s uses the block of rank r-s); every step writes its partial (O_s, lse_s) into
+  slot s of a stacked buffer and ONE pass at the end merges the P partials with their logsumexp (2 bytes read per
+  element and partial, instead of a 10-byte read-modify-write of an fp32 accumulator after every step).  The blocks travel over NVLink/NVSwitch in one of two ways: `transport="peer"` (default on a
   single node): every rank publishes its block in a CUDA-IPC buffer and the others PULL it with the copy
   engines, which needs no SM; `transport="p2p"`: NCCL send/recv through torch.distributed (also what the CPU/gloo
   tests of the schedule use).  Causal runs use the zig-zag partition (rank r owns
@@ -65,13 +66,9 @@ class _CudaBackend:
         from . import ops
         ops.attention_forward(q, k, v, causal=causal, out=out, lse=lse)
 
-    def merge(self, o_acc, lse_acc, o_part, lse_part):
+    def combine(self, o_parts, lse_parts):
         from . import ops
-        ops.merge_partial(o_acc, lse_acc, o_part, lse_part)
-
-    def finalize(self, o_acc, dtype):
-        from . import ops
-        return ops.cast_output(o_acc, dtype)
+        return ops.combine_partials(o_parts, lse_parts)
 
 
 class _RingProfile:
@@ -199,7 +196,8 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
       causal:     the zig-zag partition (`zigzag_split`): local rows = [chunk r ; chunk 2P-1-r].
     Returns (O_local `[B,H,N_local,d]` in q.dtype, lse_local `[B,H,N_local]` fp32).
 
-    Step s (s = 0..P-1) works on the block owned by rank (r - s) mod P; all P-1 remote blocks are requested up
+    Step s (s = 0..P-1) works on the block owned by rank (r - s) mod P and leaves its partial in slot s; one
+    `combine_partials` pass merges the slots at the end; all P-1 remote blocks are requested up
     front, so step s never waits on step s-1's transfer.  transport: "peer" = copy-engine pulls from CUDA-IPC
     buffers (single node, no SM used), "p2p" = torch.distributed send/recv (NCCL or gloo), "auto" = "peer" for
     CUDA tensors with the built-in backend, else "p2p".  With the zig-zag layout the causal structure per step
@@ -219,10 +217,9 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
         raise ValueError("causal ring attention needs an even local length (zig-zag halves)")
     half = Nl // 2
 
-    o_acc = torch.zeros((B, H, Nl, d), dtype=torch.float32, device=q.device)
-    lse_acc = torch.full((B, H, Nl), float("-inf"), dtype=torch.float32, device=q.device)
-    o_part = torch.empty((B, H, Nl, d), dtype=q.dtype, device=q.device)
-    lse_part = torch.empty((B, H, Nl), dtype=torch.float32, device=q.device)
+    # slot s holds the partial of step s; a slot row that a step does not compute keeps lse = -inf and is skipped
+    o_parts = torch.empty((world, B, H, Nl, d), dtype=q.dtype, device=q.device)
+    lse_parts = torch.full((world, B, H, Nl), float("-inf"), dtype=torch.float32, device=q.device)
 
     own_k, own_v = k.contiguous(), v.contiguous()
     blocks = [(own_k, own_v)] + [(torch.empty_like(own_k), torch.empty_like(own_v)) for _ in range(world - 1)]
@@ -251,6 +248,7 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
         if prof:
             prof.mark(f"s{step}:kv_ready")
         cur_k, cur_v = blocks[step]
+        o_part, lse_part = o_parts[step], lse_parts[step]
 
         if not causal or src == rank:
             be.attention(q, cur_k, cur_v, causal and src == rank, o_part, lse_part)
@@ -259,16 +257,15 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
             be.attention(q, cur_k[:, :, :half], cur_v[:, :, :half], False, o_part, lse_part)
         else:
             # only the second half of the local queries (chunk 2P-1-r) sees the visiting block
-            lse_part[:, :, :half].fill_(float("-inf"))
             be.attention(q[:, :, half:], cur_k, cur_v, False, o_part[:, :, half:], lse_part[:, :, half:])
         if prof:
             prof.mark(f"s{step}:attn_done")
-        be.merge(o_acc, lse_acc, o_part, lse_part)
-        if prof:
-            prof.mark(f"s{step}:merge_done")
 
-    out = be.finalize(o_acc, q.dtype)
+    if world == 1:
+        out, lse = o_parts[0], lse_parts[0]
+    else:
+        out, lse = be.combine(o_parts, lse_parts)
     if prof:
-        prof.mark("finalize_done")
+        prof.mark("combine_done")
         prof.report(rank)
-    return out, lse_acc
+    return out, lse

@@ -125,6 +125,16 @@ int fa_b200_forward_fp16(const void* Q, const void* K, const void* V, void* O,
 int fa_b200_merge_partial(float* O_acc, float* lse_acc, const void* O_part, const float* lse_part,
                           int64_t rows, int d, int dtype, void* stream);
 
+/* Merge `nparts` attention partials over disjoint key sets in one pass (what the ring driver runs once at the end
+ * of a forward; same arithmetic as the split-KV combine):
+ *   lse = log(sum_s exp(lse_s));   O = sum_s exp(lse_s - lse) * O_s
+ * O_parts is dtype [nparts, rows, d], lse_parts fp32 [nparts, rows]; O is dtype [rows, d], lse fp32 [rows] (optional).
+ * A partial whose lse_s is -inf for a row is skipped for that row (its O_s row is never read, so it may be
+ * uninitialised); rows with no finite partial give O = 0, lse = -inf.  HBM-bound: reads (finite partials) * 2 bytes and
+ * writes 2 bytes per element, against 10 bytes per element and partial for the incremental fa_b200_merge_partial. */
+int fa_b200_combine_partials(const void* O_parts, const float* lse_parts, int nparts, void* O, float* lse,
+                             int64_t rows, int d, int dtype, void* stream);
+
 /* Final cast of the fp32 ring accumulator to dtype: O[rows,d] = (dtype) O_acc[rows,d]. */
 int fa_b200_cast_output(void* O, const float* O_acc, int64_t rows, int d, int dtype, void* stream);
 

@@ -354,6 +354,33 @@ def test_split_kv_schedule(fa, B, H, N, Nkv, d, dtype, causal):
     assert (o.float() - o1.float()).abs().max().item() <= O_TOL
 
 
+@pytest.mark.parametrize("dtype,d", [("bf16", 128), ("fp16", 64)])
+def test_combine_partials_kernel(fa, dtype, d):
+    """attention over [K1;K2;K3] == one-pass combine of the three partials (what the ring driver runs at the end);
+    slot rows whose lse is -inf are skipped even when their O rows hold NaN."""
+    from oracle import oracle
+    B, H, N = 1, 3, 520
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, 1200, d))
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, _dt(dtype)) for x in (q, k, v))
+    o_parts = torch.full((4, B, H, N, d), float("nan"), dtype=_dt(dtype), device=dev)
+    lse_parts = torch.full((4, B, H, N), float("-inf"), dtype=torch.float32, device=dev)
+    for s_, (lo, hi) in enumerate(((0, 384), (384, 1000), (1000, 1200))):
+        fa.attention_forward(tq, tk[:, :, lo:hi], tv[:, :, lo:hi], out=o_parts[s_], lse=lse_parts[s_])
+    # slot 3: only the second half of the rows takes part (as in the zig-zag causal ring), against keys 0..100 again
+    # with its lse pushed down by 50 so that it does not change the result beyond rounding
+    half = N // 2
+    fa.attention_forward(tq[:, :, half:], tk[:, :, :100], tv[:, :, :100], out=o_parts[3][:, :, half:],
+                         lse=lse_parts[3][:, :, half:])
+    lse_parts[3][:, :, half:] -= 50.0
+    n0 = fa.launch_count()
+    o, lse = fa.combine_partials(o_parts, lse_parts)
+    torch.cuda.synchronize()
+    assert fa.launch_count() == n0 + 1
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v)
+    _check(o.float().cpu().numpy(), lse.cpu().numpy(), o_ref, lse_ref)
+
+
 def test_merge_partial_kernel(fa):
     """attention over [K1;K2] == merge(attention(K1), attention(K2)) (the ring-attention identity)."""
     from oracle import oracle

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class OracleBackend:
-    """CPU stand-in with the same three calls as the CUDA backend, built on the oracle."""
+    """CPU stand-in with the same two calls as the CUDA backend, built on the oracle."""
 
     def attention(self, q, k, v, causal, out, lse):
         from oracle import oracle
@@ -22,14 +22,15 @@ class OracleBackend:
         out.copy_(torch.from_numpy(o).to(out.dtype))
         lse.copy_(torch.from_numpy(s))
 
-    def merge(self, o_acc, lse_acc, o_part, lse_part):
+    def combine(self, o_parts, lse_parts):
         from oracle import oracle
-        o, s = oracle.merge_partial(o_acc.numpy(), lse_acc.numpy(), o_part.float().numpy(), lse_part.numpy())
-        o_acc.copy_(torch.from_numpy(o).view_as(o_acc))
-        lse_acc.copy_(torch.from_numpy(s).view_as(lse_acc))
-
-    def finalize(self, o_acc, dtype):
-        return o_acc.to(dtype)
+        o = np.zeros(o_parts.shape[1:], np.float32)
+        s = np.full(lse_parts.shape[1:], -np.inf, np.float32)
+        for i in range(o_parts.shape[0]):
+            o_i = np.nan_to_num(o_parts[i].float().numpy())      # rows a step skipped are uninitialised (lse = -inf)
+            o, s = oracle.merge_partial(o, s, o_i, lse_parts[i].numpy())
+            o, s = o.reshape(o_parts.shape[1:]), s.reshape(lse_parts.shape[1:])
+        return torch.from_numpy(o).to(o_parts.dtype), torch.from_numpy(s)
 
 
 def _worker(rank, world, port, causal, N, d, q_out):
