@@ -437,6 +437,53 @@ def _full_inputs(B, H, N, d, dtype, seed=7):  # noqa: E302 (defined below its fi
     return q, k, v
 
 
+def test_more_bh_slices_than_the_reference_grid_allows(fa):
+    """The reference launches grid(Tr, B*H) (main.cu:381), so B*H is capped at 65535 (gridDim.y); here the (b,h)
+    slices are items of a 1-D, hardware-scheduled grid.  66000 slices of a single ragged tile each, complete oracle
+    check on a sample of slices, and every slice checked for the causal first-row identity O[0] == V[0]."""
+    from oracle import oracle
+    B, H, N, d = 2, 33000, 40, 64
+    q, k, v = _full_inputs(B, H, N, d, torch.float16, seed=11)
+    o, lse = fa.attention_forward(q, k, v, causal=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert torch.equal(o[:, :, 0], v[:, :, 0])
+    for (b, h) in ((0, 0), (0, 32999), (1, 0), (1, 32535), (1, 32999)):     # b*H + h = 65535 included
+        qn, kn, vn = (t[b:b + 1, h:h + 1].float().cpu().numpy() for t in (q, k, v))
+        o_ref, lse_ref, _, _ = oracle.attention(qn, kn, vn, causal=True)
+        _check(o[b:b + 1, h:h + 1].float().cpu().numpy(), lse[b:b + 1, h:h + 1].cpu().numpy(), o_ref, lse_ref)
+
+
+@pytest.mark.parametrize("N", [65536])
+def test_long_sequence_single_gpu_properties(fa, N):
+    """One head pair at the sequence length a c5 ring rank sees over a whole forward (causal, 512 K/V tiles per item,
+    256 items per head): sampled rows vs the oracle, first-row identity, and split-key merge identity."""
+    from oracle import oracle
+    B, H, d = 1, 2, 128
+    q, k, v = _full_inputs(B, H, N, d, torch.bfloat16, seed=13)
+    o, lse = fa.attention_forward(q, k, v, causal=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert torch.equal(o[:, :, 0], v[:, :, 0])
+    qn, kn, vn = (t[:, 1:2].float().cpu().numpy() for t in (q, k, v))
+    for r0 in (0, 32704, N - 64):
+        o_ref, lse_ref, _, _ = oracle.attention(qn, kn, vn, causal=True, row_begin=r0, row_end=r0 + 64)
+        got, gl = o[0, 1, r0:r0 + 64].float().cpu().numpy(), lse[0, 1, r0:r0 + 64].cpu().numpy()
+        assert np.abs(got - o_ref[0, 0, r0:r0 + 64]).max() <= O_TOL
+        assert (np.abs(gl - lse_ref[0, 0, r0:r0 + 64]) / np.maximum(1, np.abs(lse_ref[0, 0, r0:r0 + 64]))).max() <= LSE_TOL
+    # the last 4096 queries against the keys cut in two: combine(partials) == the full causal result for those rows
+    qt = q[:, :, N - 4096:]
+    parts = torch.empty((2, B, H, 4096, d), dtype=torch.bfloat16, device=q.device)
+    lses = torch.empty((2, B, H, 4096), dtype=torch.float32, device=q.device)
+    cut = N - 4096
+    fa.attention_forward(qt, k[:, :, :cut], v[:, :, :cut], causal=False, out=parts[0], lse=lses[0])
+    fa.attention_forward(qt, k[:, :, cut:], v[:, :, cut:], causal=True, out=parts[1], lse=lses[1])
+    oc, lc = fa.combine_partials(parts, lses)
+    torch.cuda.synchronize()
+    assert (oc.float() - o[:, :, N - 4096:].float()).abs().max().item() <= O_TOL
+    assert ((lc - lse[:, :, N - 4096:]).abs() / lse[:, :, N - 4096:].abs().clamp(min=1.0)).max().item() <= LSE_TOL
+
+
 @pytest.mark.parametrize("causal", [False, True])
 def test_full_size_c3_c4_properties(fa, causal):
     """B=4 H=32 N=8192 d=128 bf16 (BASELINE c3 / c4): sampled rows vs the oracle, (b,h)-shard equivalence
