@@ -2,7 +2,7 @@
 import sys
 names = ["s0_ready", "s0_ld", "s0_pA", "s0_pB", "s1_ready", "s1_ld", "s1_pA", "s1_pB",
          "pv0A", "pv0B", "qk0", "pv1A", "pv1B", "qk1", "s0_max", "s1_max"]
-rows = [[int(x) for x in l.split()] for l in open(sys.argv[1]) if l.strip() and not l.startswith(("I ", "#"))]
+rows = [[int(x) for x in l.split()] for l in open(sys.argv[1]) if l.strip() and not l.startswith(("I ", "#", "B2"))]
 t0 = min(v for r in rows for v in r if v > 0)
 print("j    " + " ".join(f"{n:>8s}" for n in names))
 for j, r in enumerate(rows[:int(sys.argv[2]) if len(sys.argv) > 2 else 24]):
