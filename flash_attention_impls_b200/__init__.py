@@ -20,6 +20,7 @@ from .ops import (  # noqa: F401
 )
 from .parallel import (  # noqa: F401
     bh_shard_range,
+    release_peer_buffers,
     ring_attention,
     zigzag_gather,
     zigzag_split,
@@ -29,5 +30,5 @@ __all__ = [
     "attention_forward", "flash_attention", "flash_attention_with_stats", "flash_attention_forward",
     "flash_attention_cutlass_dispatch", "flash_attention_forward_dispatch",
     "flash_attention_small_tile_dispatch", "attention_reference_dispatch", "merge_partial", "combine_partials", "cast_output", "HostPipeline",
-    "ring_attention", "zigzag_split", "zigzag_gather", "bh_shard_range", "launch_count", "load",
+    "ring_attention", "release_peer_buffers", "zigzag_split", "zigzag_gather", "bh_shard_range", "launch_count", "load",
 ]

@@ -176,7 +176,32 @@ class _PeerRing:
         return events
 
 
+    def close(self):
+        """Unmaps the peers' buffers and frees this rank's publish buffers (collective: every rank must call it,
+        after a barrier, so that nobody is still pulling)."""
+        lib = self.lib.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for r, ptrs in enumerate(self.peers):
+                if r != self.rank:
+                    for p_ in ptrs:
+                        lib.fa_b200_peer_close(p_)
+            for p_ in self.mine:
+                lib.fa_b200_peer_free(p_)
+        self.peers, self.mine = [], []
+
+
 _peer_rings = {}
+
+
+def release_peer_buffers(group: Optional[dist.ProcessGroup] = None) -> None:
+    """Frees the CUDA-IPC publish buffers the "peer" transport caches per (block size, group, device).  Collective
+    over `group`; call it before destroying the process group if the buffers should not live until process exit."""
+    if not _peer_rings:
+        return
+    dist.barrier(group)
+    for key in [k for k in _peer_rings if k[1] == id(group)]:
+        _peer_rings.pop(key).close()
 
 
 def _peer_ring_for(k, group):

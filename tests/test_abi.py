@@ -86,6 +86,27 @@ def test_merge_and_cast_validation():
     assert lib.fa_b200_cast_output(0x1000, 0x1000, 4, 64, 5, None) == 4
 
 
+def test_combine_and_peer_validation():
+    lib = _lib.load()
+    assert lib.fa_b200_combine_partials(None, None, 2, None, None, 4, 64, 1, None) == 1
+    assert lib.fa_b200_combine_partials(0x1000, 0x1000, 0, 0x1000, None, 4, 64, 1, None) == 2       # nparts
+    assert lib.fa_b200_combine_partials(0x1000, 0x1000, 2, 0x1000, None, 4, 60, 1, None) == 2       # d % 8
+    assert lib.fa_b200_combine_partials(0x1000, 0x1000, 2, 0x1000, None, 1 << 31, 64, 1, None) == 2  # rows < 2^31
+    assert lib.fa_b200_combine_partials(0x1000, 0x1000, 2, 0x1000, None, 4, 64, 9, None) == 4       # dtype
+    assert lib.fa_b200_combine_partials(0x1008, 0x1000, 2, 0x1000, None, 4, 64, 1, None) == 5       # alignment
+    assert lib.fa_b200_peer_alloc(0, None, None) == 1
+    assert lib.fa_b200_peer_open(None, None) == 1
+    assert lib.fa_b200_copy_async(None, None, 16, None) == 1
+    assert lib.fa_b200_peer_free(None) == 0 and lib.fa_b200_peer_close(None) == 0      # NULL is a no-op, like cudaFree
+
+
+def test_precise_flag_is_part_of_the_parameter_block():
+    """`precise` is the last field; a zeroed block means the default single 16-bit P."""
+    p = _params()
+    assert p.precise == 0
+    assert _lib.FaB200Params.precise.offset == ctypes.sizeof(_lib.FaB200Params) - 8
+
+
 def test_no_cpu_fallback_in_python_surface():
     import torch
     import flash_attention_impls_b200 as fa
