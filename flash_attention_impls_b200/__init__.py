@@ -5,7 +5,9 @@ mirror of the reference's operator interface plus the multi-GPU drivers ((b,h) s
 """
 from ._lib import FaB200Error, LIB_PATH, launch_count, load  # noqa: F401
 from .ops import (  # noqa: F401
+    FlashAttnFunction,
     HostPipeline,
+    attention_backward,
     attention_forward,
     attention_reference_dispatch,
     cast_output,
@@ -27,7 +29,7 @@ from .parallel import (  # noqa: F401
 )
 
 __all__ = [
-    "attention_forward", "flash_attention", "flash_attention_with_stats", "flash_attention_forward",
+    "attention_forward", "attention_backward", "FlashAttnFunction", "flash_attention", "flash_attention_with_stats", "flash_attention_forward",
     "flash_attention_cutlass_dispatch", "flash_attention_forward_dispatch",
     "flash_attention_small_tile_dispatch", "attention_reference_dispatch", "merge_partial", "combine_partials", "cast_output", "HostPipeline",
     "ring_attention", "release_peer_buffers", "zigzag_split", "zigzag_gather", "bh_shard_range", "launch_count", "load",

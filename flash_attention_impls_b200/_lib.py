@@ -23,7 +23,7 @@ STATUS = {
 # every symbol include/fa_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
     "fa_b200_forward", "fa_b200_workspace_bytes", "fa_b200_forward_legacy", "fa_b200_forward_fp16", "fa_b200_merge_partial",
-    "fa_b200_combine_partials", "fa_b200_cast_output", "fa_b200_host_ctx_create", "fa_b200_forward_host", "fa_b200_host_ctx_sync",
+    "fa_b200_combine_partials", "fa_b200_cast_output", "fa_b200_backward", "fa_b200_host_ctx_create", "fa_b200_forward_host", "fa_b200_host_ctx_sync",
     "fa_b200_host_ctx_elapsed_ms", "fa_b200_host_ctx_destroy", "fa_b200_peer_alloc", "fa_b200_peer_free", "fa_b200_peer_open",
     "fa_b200_peer_close", "fa_b200_copy_async", "fa_b200_work_item", "fa_b200_launch_count", "fa_b200_last_error", "fa_b200_status_string",
     "fa_b200_version",
@@ -44,6 +44,16 @@ class FaB200Params(Structure):
         ("stream", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("precise", c_int),
+    ]
+
+
+class FaB200BwdParams(Structure):
+    """Mirror of `struct fa_b200_bwd_params` (include/fa_b200.h)."""
+    _fields_ = [
+        ("Q", c_void_p), ("K", c_void_p), ("V", c_void_p), ("O", c_void_p), ("dO", c_void_p), ("lse", c_void_p),
+        ("dQ", c_void_p), ("dK", c_void_p), ("dV", c_void_p), ("delta", c_void_p),
+        ("B", c_int), ("H", c_int), ("N", c_int), ("d", c_int), ("dtype", c_int), ("causal", c_int),
+        ("softmax_scale", c_float), ("stream", c_void_p),
     ]
 
 
@@ -77,6 +87,8 @@ def load() -> ctypes.CDLL:
     lib.fa_b200_forward_fp16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                          c_void_p]
     lib.fa_b200_forward_fp16.restype = c_int
+    lib.fa_b200_backward.argtypes = [POINTER(FaB200BwdParams)]
+    lib.fa_b200_backward.restype = c_int
     lib.fa_b200_merge_partial.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.fa_b200_merge_partial.restype = c_int
     lib.fa_b200_combine_partials.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]

@@ -20,6 +20,7 @@
 
 #include "../../include/fa_b200.h"
 #include "fa_fwd_sm100.cuh"
+#include "fa_bwd_sm100.cuh"
 
 namespace fa {
 int launch_split_combine(const void* O_part, const float* lse_part, const float* m_part, void* O, float* lse,
@@ -165,6 +166,27 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
 #endif
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return FA_B200_OK;
+}
+
+template <int D, bool kBF16, bool kCausal, bool kDQ>
+int launch_bwd(const CUtensorMap& f1, const CUtensorMap& f2, const CUtensorMap& t1, const CUtensorMap& t2,
+               const CUtensorMap& o1, const CUtensorMap& o2, const fa::BwdArgs& args, long long grid, cudaStream_t stream) {
+  auto kern = fa::fa_bwd_sm100_kernel<D, kBF16, kCausal, kDQ>;
+  constexpr int smem = fa::BwdTraits<D>::kSmemBytes;
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load() & bit)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(bwd, smem=%d): %s", smem, cudaGetErrorString(e));
+    configured.fetch_or(bit);
+  }
+  kern<<<dim3((unsigned)grid), dim3(fa::kBwdThreads), smem, stream>>>(f1, f2, t1, t2, o1, o2, args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "backward kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1);
   return FA_B200_OK;
 }
@@ -416,6 +438,91 @@ int fa_b200_forward_fp16(const void* Q, const void* K, const void* V, void* O, i
   p.dtype = FA_B200_FP16;
   p.stream = stream;
   return fa_b200_forward(&p);
+}
+
+int fa_b200_backward(const fa_b200_bwd_params* p) {
+  if (!p) return fail(FA_B200_ERR_NULL, "params is NULL");
+  if (!p->Q || !p->K || !p->V || !p->O || !p->dO || !p->lse || !p->dQ || !p->dK || !p->dV || !p->delta)
+    return fail(FA_B200_ERR_NULL, "backward: Q, K, V, O, dO, lse, dQ, dK, dV and delta must be non-NULL");
+  if (p->B <= 0 || p->H <= 0 || p->N <= 0) return fail(FA_B200_ERR_SHAPE, "B, H, N must be positive (got %d, %d, %d)", p->B, p->H, p->N);
+  const int d = p->d;
+  if (d != 32 && d != 64 && d != 128) return fail(FA_B200_ERR_HEAD_DIM, "unsupported head_dim %d (supported: 32, 64, 128)", d);
+  if (p->dtype != FA_B200_FP16 && p->dtype != FA_B200_BF16) return fail(FA_B200_ERR_DTYPE, "dtype must be FA_B200_FP16 or FA_B200_BF16");
+  const void* ptrs[] = {p->Q, p->K, p->V, p->O, p->dO, p->dQ, p->dK, p->dV};
+  for (const void* q : ptrs)
+    if (reinterpret_cast<uintptr_t>(q) & 15u) return fail(FA_B200_ERR_ALIGNMENT, "backward: tensors must be 16-byte aligned");
+  const long long BH = (long long)p->B * p->H;
+  const int num_tiles = (p->N + fa::kBlockM - 1) / fa::kBlockM;
+  if (BH * num_tiles > 0x7fffffffLL) return fail(FA_B200_ERR_SHAPE, "backward: too many tiles");
+  int rc = check_device();
+  if (rc) return rc;
+
+  const long long sn = d, sh = (long long)p->N * d, sb = (long long)p->H * p->N * d;
+  CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
+  unsigned perm = 0, perm2 = 0;
+  if ((rc = make_tmap(&tq, &perm, p->Q, p->dtype, d, p->N, p->H, p->B, sn, sh, sb))) return rc;
+  const void* bases[] = {p->K, p->V, p->dO, p->dQ, p->dK, p->dV};
+  CUtensorMap* maps[] = {&tk, &tv, &tdo, &tdq, &tdk, &tdv};
+  for (int i = 0; i < 6; ++i) {
+    if ((rc = make_tmap(maps[i], &perm2, bases[i], p->dtype, d, p->N, p->H, p->B, sn, sh, sb))) return rc;
+    if (perm2 != perm) return fail(FA_B200_ERR_DRIVER, "backward: inconsistent tensor-map axis order");
+  }
+  const float scale = (p->softmax_scale != 0.f) ? p->softmax_scale : 1.0f / sqrtf((float)d);
+  fa::BwdArgs a{};
+  a.lse = p->lse;
+  a.delta = p->delta;
+  a.N = p->N;
+  a.H = p->H;
+  a.num_tiles = num_tiles;
+  a.scale = scale;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.perm = perm;
+  const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;
+  if (d >= 64) {
+    a.desc_k = fa::umma_desc_hi_bits(16, 1024, 2);
+    a.desc_mn = fa::umma_desc_hi_bits(fa::FwdTraits<128>::kBoxBytes, 1024, 2);
+  } else {
+    a.desc_k = fa::umma_desc_hi_bits(16, 512, 4);
+    a.desc_mn = fa::umma_desc_hi_bits(fa::FwdTraits<32>::kBoxBytes, 512, 4);
+  }
+  a.idesc_ss = fa::umma_idesc(fmt, 0, 0, 128, 128);
+  a.idesc_ts = fa::umma_idesc(fmt, 0, 1, 128, (unsigned)d);
+
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
+  const bool bf16 = p->dtype == FA_B200_BF16;
+  const bool causal = p->causal != 0;
+  // 1. delta = rowsum(dO o O)
+  {
+    const long long rows = BH * p->N;
+    const long long total = rows * (d / 8);
+    long long blocks = std::min<long long>((total + 255) / 256, 148LL * 8);
+    if (bf16)
+      fa::bwd_delta_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)p->O, (const uint4*)p->dO, p->delta, rows, d);
+    else
+      fa::bwd_delta_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)p->O, (const uint4*)p->dO, p->delta, rows, d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "delta kernel launch: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+  }
+  const long long grid = BH * num_tiles;
+  // 2. dQ kernel: fixed (Q, dO), streamed (K, V), out dQ;  3. dK/dV kernel: fixed (K, V), streamed (Q, dO), out dK (dS^T Q), dV
+#define FA_BWD(D_, BF_, C_)                                                                 \
+  do {                                                                                      \
+    rc = launch_bwd<D_, BF_, C_, true>(tq, tdo, tk, tv, tdq, tdq, a, grid, stream);         \
+    if (!rc) rc = launch_bwd<D_, BF_, C_, false>(tk, tv, tq, tdo, tdk, tdv, a, grid, stream); \
+  } while (0)
+  if (d == 128) {
+    if (bf16) { if (causal) FA_BWD(128, true, true); else FA_BWD(128, true, false); }
+    else      { if (causal) FA_BWD(128, false, true); else FA_BWD(128, false, false); }
+  } else if (d == 32) {
+    if (bf16) { if (causal) FA_BWD(32, true, true); else FA_BWD(32, true, false); }
+    else      { if (causal) FA_BWD(32, false, true); else FA_BWD(32, false, false); }
+  } else {
+    if (bf16) { if (causal) FA_BWD(64, true, true); else FA_BWD(64, true, false); }
+    else      { if (causal) FA_BWD(64, false, true); else FA_BWD(64, false, false); }
+  }
+#undef FA_BWD
+  return rc;
 }
 
 uint64_t fa_b200_launch_count(void) { return g_launches.load(); }

@@ -118,16 +118,67 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
     return out, lse
 
 
+def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor,
+                       do: torch.Tensor, *, causal: bool = False, softmax_scale: Optional[float] = None):
+    """(dQ, dK, dV) of O = softmax(Q K^T scale [+ causal mask]) V for the upstream gradient `do`, from the forward's
+    output `o` and logsumexp `lse` (reference: FA2-triton.py:98-170).  Dense [B,H,N,d]
+    fp16/bf16 CUDA tensors with N_kv == N; three launches of libfa_b200.so (fa_b200_backward), no atomics."""
+    _require_cuda(q, k, v, o, lse, do)
+    B, H, N, d = q.shape
+    for t_, name in ((k, "k"), (v, "v"), (o, "o"), (do, "do")):
+        if t_.shape != q.shape or t_.dtype != q.dtype:
+            raise ValueError(f"{name} must have q's shape and dtype (backward supports N_kv == N only)")
+    if lse.shape != (B, H, N) or lse.dtype != torch.float32:
+        raise ValueError("lse must be fp32 [B,H,N]")
+    q, k, v, o, do, lse = (t_.contiguous() for t_ in (q, k, v, o, do, lse))
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    delta = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
+    p = _lib.FaB200BwdParams()
+    p.Q, p.K, p.V, p.O, p.dO, p.lse = (t_.data_ptr() for t_ in (q, k, v, o, do, lse))
+    p.dQ, p.dK, p.dV, p.delta = dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr()
+    p.B, p.H, p.N, p.d = B, H, N, d
+    p.dtype = _dtype_code(q)
+    p.causal = 1 if causal else 0
+    p.softmax_scale = float(softmax_scale) if softmax_scale else 0.0
+    p.stream = _stream_ptr(q)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().fa_b200_backward(ctypes.byref(p)))
+    return dq, dk, dv
+
+
+class FlashAttnFunction(torch.autograd.Function):
+    """Mirror of the reference's `_FlashAttnFn` (FA2-triton.py:173-237): forward saves (q, k, v) and the row
+    statistics, backward returns (dQ, dK, dV, None).  The statistics are kept as one logsumexp instead of (m, l)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, causal: bool):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, lse = attention_forward(q, k, v, causal=causal)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.causal = causal
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        dq, dk, dv = attention_backward(q, k, v, o, lse, do.contiguous(), causal=ctx.causal)
+        return dq, dk, dv, None
+
+
 def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False) -> torch.Tensor:
     """Drop-in for the reference's `flash_attention(q, k, v, causal)` (FA2-triton.py:240-244).
 
-    Like the reference, fp32 inputs are down-cast to fp16 for the kernel and the result is cast back.
+    Like the reference, fp32 inputs are down-cast to fp16 for the kernel and the result is cast back; when an input
+    requires grad the call goes through `FlashAttnFunction`, as the reference's goes through `_FlashAttnFn`.
     """
     _require_cuda(q, k, v)
     orig = q.dtype
     if orig == torch.float32:
         q, k, v = q.half(), k.half(), v.half()
-    o, _ = attention_forward(q.contiguous(), k.contiguous(), v.contiguous(), causal=causal, return_lse=False)
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        o = FlashAttnFunction.apply(q, k, v, causal)
+    else:
+        o, _ = attention_forward(q.contiguous(), k.contiguous(), v.contiguous(), causal=causal, return_lse=False)
     return o.to(orig) if orig == torch.float32 else o
 
 

@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define FA_B200_VERSION_MAJOR 0
-#define FA_B200_VERSION_MINOR 3
+#define FA_B200_VERSION_MINOR 4
 
 /* status codes (0 = ok).  The reference returns void and prints to stderr
  * (flash_attn_cutlass.cu:540-542, :510-514); the C ABI returns codes instead. */
@@ -137,6 +137,32 @@ int fa_b200_combine_partials(const void* O_parts, const float* lse_parts, int np
 
 /* Final cast of the fp32 ring accumulator to dtype: O[rows,d] = (dtype) O_acc[rows,d]. */
 int fa_b200_cast_output(void* O, const float* O_acc, int64_t rows, int d, int dtype, void* stream);
+
+/* ---- backward (reference: code/triton_fa2/FA2-triton.py:98-170, :207-237) ---------------------
+ * dQ, dK, dV of O = softmax(Q K^T scale [+ causal mask]) V for an upstream gradient dO, from the forward's O and
+ * logsumexp (for the reference's saved statistics: lse = m + ln l, FA2-triton.py:203).  Dense [B,H,N,d] tensors, N_kv == N.
+ * Three launches: delta = rowsum(dO o O) (HBM-bound), a dQ kernel and a dK/dV kernel (tcgen05; see
+ * flash_attention_impls_b200/csrc/fa_bwd_sm100.cuh).  Every output element has one writer: no atomics (the reference
+ * accumulates dK/dV with fp16 atomic adds, :164-167), deterministic, outputs are overwritten, not accumulated into.
+ * `delta` is caller-provided fp32 scratch of B*H*N elements. */
+typedef struct fa_b200_bwd_params {
+  const void* Q;     /* [B,H,N,d] dtype */
+  const void* K;
+  const void* V;
+  const void* O;     /* forward output */
+  const void* dO;    /* upstream gradient, same layout */
+  const float* lse;  /* [B,H,N] forward logsumexp */
+  void* dQ;          /* [B,H,N,d] dtype, written */
+  void* dK;
+  void* dV;
+  float* delta;      /* [B,H,N] fp32 scratch */
+  int B, H, N, d;
+  int dtype;         /* enum fa_b200_dtype */
+  int causal;
+  float softmax_scale; /* 0 => 1/sqrt(d) */
+  void* stream;
+} fa_b200_bwd_params;
+int fa_b200_backward(const fa_b200_bwd_params* p);
 
 /* ---- host-buffer path (what bench.py's `e2e` figure times) -------------------------------------------------
  * The reference's drivers keep Q, K, V on the host and copy them over before launching (main.cu:403-405,

@@ -89,6 +89,48 @@ def attention_f64(q, k, v, causal=False, scale=None):
     return o, lse, l, m
 
 
+def attention_backward_f64(q, k, v, do, causal=False, scale=None):
+    """Gradients of O = softmax(Q K^T scale [+ causal mask]) V w.r.t. Q, K, V for an upstream gradient dO, in numpy
+    float64, per (b,h) slice to bound memory.  This is the mathematics the reference's Triton backward recomputes
+    (FA2-triton.py:98-170: P from the saved row statistics, dV = P^T dO, dP = dO V^T, dS, dQ = dS K, dK = dS^T Q) with
+    the standard softmax Jacobian
+        dS_ij = scale * P_ij * (dP_ij - sum_k P_ik dP_ik),     sum_k P_ik dP_ik = dO_i . O_i
+    The reference kernel itself forms `(dP - sum_block(dP*P) * P) * scale` with the sum taken over one 128-key block
+    (FA2-triton.py:158-159), which is not this Jacobian, and the reference never checks its backward (SURVEY.md section 4);
+    the pin for this function is therefore torch.autograd through the reference's own `sdpa_reference`
+    (tests/golden/make_golden_bwd.py -> tests/golden/sdpa_bwd_golden.npz).
+    Returns (dQ, dK, dV, delta) as float64, delta[b,h,i] = dO_i . O_i."""
+    q = np.asarray(q, np.float64); k = np.asarray(k, np.float64); v = np.asarray(v, np.float64)
+    do = np.asarray(do, np.float64)
+    B, H, N, d = q.shape
+    Nkv = k.shape[2]
+    sc = scale if scale else 1.0 / math.sqrt(d)
+    dq = np.zeros_like(q); dk = np.zeros_like(k); dv = np.zeros_like(v)
+    delta = np.zeros((B, H, N))
+    if causal:
+        i = np.arange(N)[:, None]; j = np.arange(Nkv)[None, :]
+        masked = j > i + (Nkv - N)
+    for b in range(B):
+        for h in range(H):
+            s = (q[b, h] @ k[b, h].T) * sc
+            if causal:
+                s = np.where(masked, -np.inf, s)
+            m = s.max(axis=-1, keepdims=True)
+            msafe = np.where(np.isfinite(m), m, 0.0)
+            e = np.exp(s - msafe)
+            l = e.sum(axis=-1, keepdims=True)
+            p = e / np.where(l > 0, l, 1.0)
+            o = p @ v[b, h]
+            dp = do[b, h] @ v[b, h].T
+            dl = (do[b, h] * o).sum(axis=-1, keepdims=True)
+            ds = p * (dp - dl) * sc
+            dq[b, h] = ds @ k[b, h]
+            dk[b, h] = ds.T @ q[b, h]
+            dv[b, h] = p.T @ do[b, h]
+            delta[b, h] = dl[:, 0]
+    return dq, dk, dv, delta
+
+
 def merge_partial(o_a, lse_a, o_b, lse_b):
     o_a = np.ascontiguousarray(o_a, np.float32).copy(); lse_a = np.ascontiguousarray(lse_a, np.float32).copy()
     o_b = np.ascontiguousarray(o_b, np.float32); lse_b = np.ascontiguousarray(lse_b, np.float32)

@@ -48,7 +48,7 @@ def test_struct_layout_matches_header():
 
 def test_version_and_status_strings():
     lib = _lib.load()
-    assert lib.fa_b200_version() == (0 << 16) | 3
+    assert lib.fa_b200_version() == (0 << 16) | 4
     assert lib.fa_b200_status_string(0) == b"ok"
     assert lib.fa_b200_status_string(3) == b"unsupported head_dim"
     assert lib.fa_b200_status_string(99) == b"unknown status"
@@ -98,6 +98,28 @@ def test_combine_and_peer_validation():
     assert lib.fa_b200_peer_open(None, None) == 1
     assert lib.fa_b200_copy_async(None, None, 16, None) == 1
     assert lib.fa_b200_peer_free(None) == 0 and lib.fa_b200_peer_close(None) == 0      # NULL is a no-op, like cudaFree
+
+
+def test_backward_validation_returns_codes_without_a_gpu():
+    lib = _lib.load()
+    assert lib.fa_b200_backward(None) == 1
+    p = _lib.FaB200BwdParams()
+    for name in ("Q", "K", "V", "O", "dO", "lse", "dQ", "dK", "dV", "delta"):
+        setattr(p, name, 0x1000)
+    p.B, p.H, p.N, p.d, p.dtype = 1, 2, 128, 64, 1
+    p.dK = None
+    assert lib.fa_b200_backward(ctypes.byref(p)) == 1          # missing output
+    p.dK = 0x1000
+    p.N = 0
+    assert lib.fa_b200_backward(ctypes.byref(p)) == 2
+    p.N, p.d = 128, 96
+    assert lib.fa_b200_backward(ctypes.byref(p)) == 3
+    p.d, p.dtype = 64, 3
+    assert lib.fa_b200_backward(ctypes.byref(p)) == 4
+    p.dtype, p.dO = 0, 0x1004
+    assert lib.fa_b200_backward(ctypes.byref(p)) == 5
+    # 10 pointers, 6 ints + float (+ padding), stream
+    assert ctypes.sizeof(_lib.FaB200BwdParams) == 10 * 8 + 8 * 4 + 8
 
 
 def test_precise_flag_is_part_of_the_parameter_block():
