@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-end style validation on one B200: GPU tests, smoke, benches (c3,c4,c2), ncu launch list + full capture,
-# the re-hosted reference cuda_fa1 driver next to the original.  (compute-sanitizer is closed on this pool.)
+# the re-hosted reference cuda_fa1 driver next to the original, backward timing.  (compute-sanitizer is closed on this pool.)
 TAG=${1:-final}
 mkdir -p gpurun_out
 L=gpurun_out/final_$TAG.log; : > $L
@@ -14,4 +14,6 @@ done
 for a in "1 8 512 64 4096 50" "8 16 1024 64 16384 20"; do
   echo "--- main_ref $a" >> $L; timeout 300 oracle/_ref/main_ref $a 2>&1 | grep -v "^Error at" >> $L; echo "exit=$?" >> $L
 done
+echo "##### backward timing (tools/bwd_time.py)" >> $L
+timeout 200 python tools/bwd_time.py >> $L 2>&1; echo "exit=$?" >> $L
 cat $L | cut -c1-250 | tail -150
