@@ -4,7 +4,7 @@ ARCH  := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo
 PKG   := flash_attention_impls_b200
 CSRC  := $(PKG)/csrc/fa_api.cu $(PKG)/csrc/fa_merge.cu $(PKG)/csrc/fa_host.cu $(PKG)/csrc/fa_ref_shims.cu
-HDRS  := $(PKG)/csrc/fa_fwd_sm100.cuh $(PKG)/csrc/sm100_ptx.cuh include/fa_b200.h
+HDRS  := $(wildcard $(PKG)/csrc/*.cuh) include/fa_b200.h
 
 all: lib oracle tools
 

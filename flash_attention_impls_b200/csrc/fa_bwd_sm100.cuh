@@ -21,8 +21,10 @@
 //   warps 0-3 : compute warpgroup, one thread per TMEM lane (score row): P / dS, then the epilogue (TMA store)
 //   warp  4   : TMA producer          warp 5 : tcgen05.mma issuer          warp 6 : TMEM allocator
 // TMEM (512 columns): S | dP | acc1 (D columns: dS x T1 = dQ or dK) | acc2 (D columns: P x T2 = dV).  The 16-bit P
-// and dS overwrite the first 64 columns of S and dP.  This first version runs one tile at a time (the tensor pipe idles
-// while the compute warpgroup works); it is the correctness baseline for the backward, not a tuned kernel.
+// and dS overwrite the first 64 columns of S and dP.  The dK/dV kernel runs one tile at a time (the tensor pipe idles
+// while the compute warpgroup works).  The dQ kernel needs no P in TMEM and no acc2, so it keeps a second dP buffer in
+// columns 384..511 and issues the score-like products of step n+1 while the compute warpgroup works on step n.
+// This is the correctness baseline for the backward, not a tuned kernel.
 #pragma once
 #include "fa_fwd_sm100.cuh"
 
@@ -97,6 +99,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_const
   const uint32_t bar_s_full = bars + 40;       //      MMA -> compute (S and dP are in TMEM)
   const uint32_t bar_p_full = bars + 48;       //      compute -> MMA (P and dS are in TMEM; 128 arrivals)
   const uint32_t bar_acc_full = bars + 56;     //      MMA -> compute (all accumulating products have landed)
+  const uint32_t bar_s_free = bars + 72;       //      compute -> MMA (dQ kernel: S is in registers; 128 arrivals)
   const uint32_t tmem_slot = bars + 64;
   const uint32_t s_stats = bars + 256;         // [2 stages][lse2 | delta][128] fp32 (dK/dV kernel only)
 
@@ -124,6 +127,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_const
     mbar_init(bar_s_full, 1);
     mbar_init(bar_p_full, 128);
     mbar_init(bar_acc_full, 1);
+    mbar_init(bar_s_free, 128);
     fence_mbar_init();
   }
   if (warp == 6) {
@@ -161,7 +165,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_const
     // =========================== MMA issuer ===========================
     const uint32_t hi_k = uint32_t(a.desc_k >> 32), lo_k = uint32_t(a.desc_k);
     const uint32_t hi_mn = uint32_t(a.desc_mn >> 32), lo_mn = uint32_t(a.desc_mn);
-    const uint32_t tS = tmem_base, tdP = tmem_base + kBlockN, tA1 = tmem_base + 2 * kBlockN, tA2 = tA1 + D;
+    const uint32_t tS = tmem_base, tdP = tmem_base + kBlockN, tA1 = tmem_base + 2 * kBlockN;
+    [[maybe_unused]] const uint32_t tA2 = tA1 + D;
     // D_tmem = A (K-major smem tile) x B^T (K-major smem tile): D/16 k-steps
     auto issue_ss = [&](uint32_t d_tmem, uint32_t sa, uint32_t sb) {
       const uint32_t a_lo = lo_k | (sa >> 4), b_lo = lo_k | (sb >> 4);
@@ -179,26 +184,65 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_const
         umma_ts(d_tmem, a_tmem + k * 8, b_lo + k * (16 * kRowBytes / 16), hi_mn, a.idesc_ts, (acc || k > 0) ? 1u : 0u);
     };
     mbar_wait(bar_f_full, 0, 600);
-    for (int n = 0; n < steps; ++n) {
-      const int s = n & 1;
-      const uint32_t sT1 = sT + (2 * s) * kTileBytes, sT2 = sT1 + kTileBytes;
-      mbar_wait(bar_t_full + 8 * s, uint32_t(n >> 1) & 1u, 610 + s);
+    if constexpr (kDQ) {
+      // The dQ kernel never needs P in TMEM (dS is all the accumulating product consumes), so S is free as soon as the
+      // compute warpgroup has it in registers, and 384 + D <= 512 columns leave room for a second dP buffer: the
+      // score-like products of step n+1 are issued while the compute warpgroup works on step n.
+      auto tdP_of = [&](int n) { return tmem_base + ((n & 1) ? 3 * kBlockN : kBlockN); };
+      mbar_wait(bar_t_full, 0, 610);
       tc_fence_after();
       if (elect_one_sync()) {
-        issue_ss(tS, sF1, sT1);     // S   = F1 T1^T
-        issue_ss(tdP, sF2, sT2);    // dP  = F2 T2^T
+        issue_ss(tS, sF1, sT);                     // S(0)
+        issue_ss(tdP_of(0), sF2, sT + kTileBytes); // dP(0)
         umma_commit(bar_s_full);
       }
       __syncwarp();
-      mbar_wait(bar_p_full, uint32_t(n) & 1u, 620);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        issue_ts(tA1, tdP, sT1, n > 0);              // acc1 += dS x T1   (dQ or dK)
-        if (!kDQ) issue_ts(tA2, tS, sT2, n > 0);     // acc2 += P  x T2   (dV)
-        umma_commit(bar_t_empty + 8 * s);
-        if (n == steps - 1) umma_commit(bar_acc_full);
+      for (int n = 0; n < steps; ++n) {
+        const int s = n & 1;
+        if (n + 1 < steps) {
+          const int s1 = (n + 1) & 1;
+          const uint32_t sN1 = sT + (2 * s1) * kTileBytes;
+          mbar_wait(bar_t_full + 8 * s1, uint32_t((n + 1) >> 1) & 1u, 610 + s1);
+          mbar_wait(bar_s_free, uint32_t(n) & 1u, 630);     // S(n) is in the compute warpgroup's registers
+          tc_fence_after();
+          if (elect_one_sync()) {
+            issue_ss(tS, sF1, sN1);                          // S(n+1)
+            issue_ss(tdP_of(n + 1), sF2, sN1 + kTileBytes);  // dP(n+1) into the other dP buffer
+            umma_commit(bar_s_full);
+          }
+          __syncwarp();
+        }
+        mbar_wait(bar_p_full, uint32_t(n) & 1u, 620);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          issue_ts(tA1, tdP_of(n), sT + (2 * s) * kTileBytes, n > 0);   // dQ += dS(n) x K(n)
+          umma_commit(bar_t_empty + 8 * s);
+          if (n == steps - 1) umma_commit(bar_acc_full);
+        }
+        __syncwarp();
       }
-      __syncwarp();
+    } else {
+      for (int n = 0; n < steps; ++n) {
+        const int s = n & 1;
+        const uint32_t sT1 = sT + (2 * s) * kTileBytes, sT2 = sT1 + kTileBytes;
+        mbar_wait(bar_t_full + 8 * s, uint32_t(n >> 1) & 1u, 610 + s);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          issue_ss(tS, sF1, sT1);     // S^T  = K Q^T
+          issue_ss(tdP, sF2, sT2);    // dP^T = V dO^T
+          umma_commit(bar_s_full);
+        }
+        __syncwarp();
+        mbar_wait(bar_p_full, uint32_t(n) & 1u, 620);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          issue_ts(tA1, tdP, sT1, n > 0);     // dK += dS^T x Q
+          issue_ts(tA2, tS, sT2, n > 0);      // dV += P^T  x dO
+          umma_commit(bar_t_empty + 8 * s);
+          if (n == steps - 1) umma_commit(bar_acc_full);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp < 4) {
     // =========================== compute warpgroup ===========================
@@ -237,36 +281,66 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_const
       }
       mbar_wait(bar_s_full, uint32_t(n) & 1u, 700);
       tc_fence_after();
+      if constexpr (kDQ) {
+        // all of S into registers first, then hand the S columns back to the MMA warp (it issues step n+1 meanwhile);
+        // dP(n) lives in buffer n & 1 and is consumed in 32-column groups, dS written back over its first 64 columns
+        const uint32_t tdPn = tS + ((n & 1) ? 3 * kBlockN : kBlockN);
+        uint32_t sr[4][32];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t sr[32], dr[32];
-        tmem_ld32(tS + q * 32, sr);
-        tmem_ld32(tdP + q * 32, dr);
+        for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, sr[q]);
         tmem_wait_ld();
-        uint32_t pk[16], dk[16];
+        tc_fence_before();
+        mbar_arrive(bar_s_free);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          float pv[2], dv[2];
+        for (int q = 0; q < 4; ++q) {
+          uint32_t dr[32];
+          tmem_ld32(tdPn + q * 32, dr);
+          tmem_wait_ld();
+          uint32_t dk[16];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = q * 32 + 2 * k + e;
-            float l2 = lse2_r, dl = delta_r;
-            if (!kDQ) {
+          for (int k = 0; k < 16; ++k) {
+            float dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = q * 32 + 2 * k + e;
+              const bool vis = (c >= c_lo) && (c <= c_hi);
+              const float p = vis ? ex2_approx(fmaf(__uint_as_float(sr[q][2 * k + e]), a.scale_log2, -lse2_r)) : 0.f;
+              dv[e] = p * (__uint_as_float(dr[2 * k + e]) - delta_r) * a.scale;
+            }
+            dk[k] = pack2<kBF16>(dv[0], dv[1]);
+          }
+          tmem_st16(tdPn + q * 16, dk);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t sr[32], dr[32];
+          tmem_ld32(tS + q * 32, sr);
+          tmem_ld32(tdP + q * 32, dr);
+          tmem_wait_ld();
+          uint32_t pk[16], dk[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float pv[2], dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = q * 32 + 2 * k + e;
+              float l2, dl;
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l2) : "r"(st + uint32_t(c) * 4u));
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dl) : "r"(st + 512u + uint32_t(c) * 4u));
+              const bool vis = (c >= c_lo) && (c <= c_hi);
+              const float p = vis ? ex2_approx(fmaf(__uint_as_float(sr[2 * k + e]), a.scale_log2, -l2)) : 0.f;
+              pv[e] = p;
+              dv[e] = p * (__uint_as_float(dr[2 * k + e]) - dl) * a.scale;
             }
-            const bool vis = (c >= c_lo) && (c <= c_hi);
-            const float p = vis ? ex2_approx(fmaf(__uint_as_float(sr[2 * k + e]), a.scale_log2, -l2)) : 0.f;
-            pv[e] = p;
-            dv[e] = p * (__uint_as_float(dr[2 * k + e]) - dl) * a.scale;
+            pk[k] = pack2<kBF16>(pv[0], pv[1]);
+            dk[k] = pack2<kBF16>(dv[0], dv[1]);
           }
-          pk[k] = pack2<kBF16>(pv[0], pv[1]);
-          dk[k] = pack2<kBF16>(dv[0], dv[1]);
+          // 16-bit P over S columns [16q, 16q+16), dS over dP columns [16q, 16q+16): both inside column groups that
+          // are already in registers (groups <= q)
+          tmem_st16(tS + q * 16, pk);
+          tmem_st16(tdP + q * 16, dk);
         }
-        // 16-bit P over S columns [16q, 16q+16), dS over dP columns [16q, 16q+16): both inside column groups that
-        // are already in registers (groups <= q)
-        tmem_st16(tS + q * 16, pk);
-        tmem_st16(tdP + q * 16, dk);
       }
       tmem_wait_st();
       tc_fence_before();
