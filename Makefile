@@ -3,7 +3,7 @@ NVCC  ?= nvcc
 ARCH  := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo
 PKG   := flash_attention_impls_b200
-CSRC  := $(PKG)/csrc/fa_api.cu $(PKG)/csrc/fa_merge.cu $(PKG)/csrc/fa_host.cu $(PKG)/csrc/fa_ref_shims.cu
+CSRC  := $(PKG)/csrc/fa_api.cu $(PKG)/csrc/fa_merge.cu $(PKG)/csrc/fa_host.cu $(PKG)/csrc/fa_ring.cu $(PKG)/csrc/fa_ref_shims.cu
 HDRS  := $(wildcard $(PKG)/csrc/*.cuh) include/fa_b200.h
 
 all: lib oracle tools

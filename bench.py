@@ -167,6 +167,88 @@ def reference_arm(args, wl):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(torch, dev):
+    """Binds the calling thread to the CPUs NVML reports as local to this GPU, so that the pinned host buffers of
+    the e2e arm are first-touched on the GPU's own NUMA node.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        node = None
+        try:
+            for n in sorted(os.listdir("/sys/devices/system/node")):
+                if n.startswith("node") and n[4:].isdigit():
+                    with open(f"/sys/devices/system/node/{n}/cpulist") as f:
+                        first = f.read().split(",")[0].split("-")
+                    lo, hi = int(first[0]), int(first[-1])
+                    if lo <= cpus[0] <= hi:
+                        node = int(n[4:])
+        except Exception:
+            pass
+        return {"cpus": f"{cpus[0]}-{cpus[-1]} ({len(cpus)})", "numa_node": node}
+    except Exception as e:                      # affinity is an optimisation, never a requirement
+        return {"error": str(e)[:80]}
+
+
+def timed_steps(torch, step, steps, flush=None):
+    """K steps bracketed by per-step CUDA events on the current stream.  Returns (total_ms, sorted per-step ms):
+    without a flush the steps run back to back and the total is first-start -> last-end."""
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for i in range(steps):
+        if flush is not None:
+            flush.zero_()
+        ev0[i].record()
+        step()
+        ev1[i].record()
+    torch.cuda.synchronize()
+    per = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total = ev0[0].elapsed_time(ev1[-1]) if flush is None else sum(per)
+    return total, sorted(per)
+
+
+def synth(torch, shape, dtype, dev, seed):
+    """Set S distribution: Q, K ~ N(0,1), V ~ U(-0.5, 0.5), generated on the device."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    q = torch.randn(shape, generator=g, device=dev, dtype=torch.float32).to(dtype)
+    k = torch.randn(shape, generator=g, device=dev, dtype=torch.float32).to(dtype)
+    v = (torch.rand(shape, generator=g, device=dev, dtype=torch.float32) - 0.5).to(dtype)
+    return q, k, v
+
+
+def kernel_record(torch, fa, name, dev, peaks, steps):
+    """Device-timed figure of another BASELINE config on this GPU (sub-record of the line; not the headline)."""
+    B, H, N, d, dtype_name, causal = WORKLOADS[name]
+    dtype = torch.bfloat16 if dtype_name == "bf16" else torch.float16
+    q, k, v = synth(torch, (B, H, N, d), dtype, dev, 4321)
+    o = torch.empty_like(q)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+    in_bytes = 3 * q.numel() * q.element_size()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if in_bytes < (256 << 20) else None
+
+    def step():
+        fa.attention_forward(q, k, v, causal=causal, out=o, lse=lse)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    total, per = timed_steps(torch, step, steps, flush)
+    ms = sum(per) / len(per)
+    fl = flops_of(B, H, N, d, causal)
+    alg_bytes = 4 * B * H * N * d * 2 + B * H * N * 4
+    tf = fl / (ms * 1e-3) * 1e-12
+    gbs = alg_bytes / (ms * 1e-3) * 1e-9
+    return {"workload": name, "B": B, "H": H, "N": N, "d": d, "dtype": dtype_name, "causal": causal, "steps": steps,
+            "launch_ms_mean": ms, "launch_ms_min": per[0], "tflops": tf, "frac_of_measured_tensor_peak": tf / peaks["tflops"],
+            "hbm_gbs_algorithmic": gbs, "frac_of_measured_hbm_peak": gbs / peaks["hbm"],
+            "l2": "L2 flushed (512 MB write) between timed iterations" if flush is not None else "inputs exceed L2"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,8 +259,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer arm (0 = min(steps, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (c2/c4 at N=1; strong c3 and ring c5 at N>1)")
     ap.add_argument("--ring-transport", default="auto", choices=["auto", "peer", "p2p"],
-                    help="c5 only: K/V block transport (auto = CUDA-IPC peer buffers + copy-engine pulls)")
+                    help="ring attention: K/V block transport (auto = the C-ABI ring: copy-engine pulls from peer memory)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -199,6 +282,7 @@ def main():
                          "for the CPU baseline arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(torch, dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     fa.load()
@@ -208,17 +292,21 @@ def main():
     ring = args.workload == "c5" and world > 1
     peaks = load_peaks()
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- synthetic inputs (Set S distribution, generated on the device; resident before the timed region)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    if ring:
-        n_local = N // world
-        shape = (B, H, n_local, d)
-    else:
-        shape = (B, H, N, d)
-    q = torch.randn(shape, generator=g, device=dev, dtype=torch.float32).to(dtype)
-    k = torch.randn(shape, generator=g, device=dev, dtype=torch.float32).to(dtype)
-    v = (torch.rand(shape, generator=g, device=dev, dtype=torch.float32) - 0.5).to(dtype)
+    shape = (B, H, N // world, d) if ring else (B, H, N, d)
+    q, k, v = synth(torch, shape, dtype, dev, 1234 + rank)
     o = torch.empty_like(q)
     lse = torch.empty(shape[:3], dtype=torch.float32, device=dev)
 
@@ -233,11 +321,6 @@ def main():
         step_flops_total = flops_of(B, H, N, d, causal) * world  # every rank runs the full workload
         scaling = "weak"
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(args.warmup):
         step()
     barrier()
@@ -249,26 +332,12 @@ def main():
     sampler = ClockSampler(dev)
     sampler.start()
     launches0 = fa.launch_count()
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
-    for i in range(args.steps):
-        if flush is not None:
-            flush.zero_()
-        ev0[i].record()
-        step()
-        ev1[i].record()
-    torch.cuda.synchronize()
-    # without a flush the steps run back to back and the span first-start -> last-end is the step time
-    total_ms = ev0[0].elapsed_time(ev1[-1]) if flush is None else sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    total_ms, per_step = timed_steps(torch, step, args.steps, flush)
     barrier()
     launches = fa.launch_count() - launches0
     clocks = sampler.stop()
-    per_step = sorted(a.elapsed_time(b) for a, b in zip(ev0, ev1))
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
     value = step_flops_total / (ms_per_step * 1e-3) * 1e-12
 
@@ -290,43 +359,98 @@ def main():
                     "hbm_gbs_algorithmic": alg_bytes / (mean_launch_ms * 1e-3) * 1e-9, "hbm_peak_gbs": peaks["hbm"]}
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                roofline["traffic"] = json.load(f).get(args.workload)
+                tr = json.load(f)
+            roofline["traffic"] = tr.get(args.workload)
+            roofline["traffic_source"] = ("not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                          "launch from the committed ncu --set full capture, " + str(tr.get("_source")))
         except Exception:
             pass
 
     # ---- e2e: pinned host buffers -> H2D -> kernel -> D2H, through the package's public host API
-    e2e = None
-    if not args.no_e2e and not ring:
-        pipe = fa.HostPipeline(B, H, N, d, dtype, causal=causal, chunks=8, device=dev)
-        hq = torch.empty((B, H, N, d), dtype=dtype).pin_memory()
-        hk = torch.empty_like(hq).pin_memory()
-        hv = torch.empty_like(hq).pin_memory()
-        ho = torch.empty_like(hq).pin_memory()
-        hl = torch.empty((B, H, N), dtype=torch.float32).pin_memory()
-        hq.copy_(q.cpu()); hk.copy_(k.cpu()); hv.copy_(v.cpu())
+    def e2e_arm(nbh0, nbh1, total_flops):
+        """Times fa_b200_forward_host over the (b,h) slices [nbh0, nbh1) of the workload (all of them at N=1; this
+        rank's shard in the strong-scaling sub-record).  The step time is host wall clock around call + sync (what a
+        caller sees); the library's own device-event span first-H2D -> last-D2H is reported beside it."""
+        n = nbh1 - nbh0
+        pipe = fa.HostPipeline(1, n, N, d, dtype, causal=causal, chunks=min(8, n), device=dev)
+        hq = torch.empty((1, n, N, d), dtype=dtype).pin_memory()
+        hk, hv, ho = (torch.empty_like(hq).pin_memory() for _ in range(3))
+        hl = torch.empty((1, n, N), dtype=torch.float32).pin_memory()
+        src = [t.reshape(1, B * H, N, d)[:, nbh0:nbh1] for t in (q, k, v)]
+        hq.copy_(src[0].cpu()); hk.copy_(src[1].cpu()); hv.copy_(src[2].cpu())
         n_e2e = args.e2e_steps or min(args.steps, 5)
         for _ in range(2):
             pipe(hq, hk, hv, ho, hl)
             pipe.synchronize()
         barrier()
-        # every step's result is read back on the host, so each step ends with a sync; the step time is the
-        # device-side span first-H2D -> last-D2H recorded by the library around its own copies and kernels
-        e2e_ms = 0.0
+        dev_ms, t0 = 0.0, time.perf_counter()
         for _ in range(n_e2e):
             pipe(hq, hk, hv, ho, hl)
-            pipe.synchronize()
-            e2e_ms += pipe.elapsed_ms_last_call()
+            pipe.synchronize()          # the step's result is read on the host: every step ends with a sync
+            dev_ms += pipe.elapsed_ms_last_call()
+        host_ms = (time.perf_counter() - t0) * 1e3
         torch.cuda.synchronize()
-        if world > 1:
-            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
+        host_ms, dev_ms = max_over_ranks(host_ms), max_over_ranks(dev_ms)
         bi, bo = pipe.bytes_per_call()
-        e2e = {"value": step_flops_total / (e2e_ms / n_e2e * 1e-3) * 1e-12, "unit": UNIT,
-               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "ms_per_step": e2e_ms / n_e2e, "steps": n_e2e,
+        rec = {"value": total_flops / (host_ms / n_e2e * 1e-3) * 1e-12, "unit": UNIT,
+               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "ms_per_step": host_ms / n_e2e,
+               "device_span_ms_per_step": dev_ms / n_e2e, "steps": n_e2e,
+               "timer": "host wall clock around fa_b200_forward_host + fa_b200_host_ctx_sync, max over ranks; "
+                        "device_span = the library's CUDA-event span first H2D -> last D2H",
                "api": "fa_b200_forward_host (C ABI; pinned host -> 8-chunk H2D/compute/D2H pipeline on 3 streams)",
+               "host_affinity": affinity,
                "result_check": float(ho.view(-1)[:1024].float().abs().sum().item())}
+        pipe.close()
         barrier()
+        return rec
+
+    e2e = None
+    if not args.no_e2e and not ring:
+        e2e = e2e_arm(0, B * H, step_flops_total)
+
+    # ---- sub-records: the other BASELINE configs, driver-visible in the same line
+    sub = {}
+    if not args.no_sub and args.workload == "c3":
+        sub_steps = max(3, min(args.steps, 10))
+        if world == 1:
+            for name in ("c2", "c4"):
+                sub[name] = kernel_record(torch, fa, name, dev, peaks, max(sub_steps, 20))
+        else:
+            # (i) BASELINE configs[2]: c3 (batch,head)-SHARDED over the ranks - strong scaling, no collective
+            b0, b1 = fa.bh_shard_range(B * H, world, rank)
+            qs, ks, vs = (t.reshape(1, B * H, N, d)[:, b0:b1] for t in (q, k, v))
+            os_ = o.reshape(1, B * H, N, d)[:, b0:b1]
+            ls_ = lse.reshape(1, B * H, N)[:, b0:b1]
+
+            def shard_step():
+                fa.attention_forward(qs, ks, vs, causal=causal, out=os_, lse=ls_)
+            for _ in range(3):
+                shard_step()
+            barrier()
+            smp = ClockSampler(dev); smp.start()
+            t_ms, per = timed_steps(torch, shard_step, sub_steps)
+            barrier()
+            clk = smp.stop()
+            t_ms = max_over_ranks(t_ms) / sub_steps
+            full_ms = sum(per_step) / len(per_step)               # this rank's full-c3 launch time from the headline run
+            tf_total = flops_of(B, H, N, d, causal) / (t_ms * 1e-3) * 1e-12
+            sub["strong_c3"] = {
+                "config": "BASELINE configs[2]: B=4 H=32 N=8192 d=128 bf16 non-causal, (b,h) slices split over the ranks "
+                          "(bh_shard_range), no collective", "scaling": "strong", "n_gpus": world,
+                "bh_per_gpu": b1 - b0, "steps": sub_steps, "ms_per_step": t_ms, "value": tf_total, "unit": UNIT,
+                "per_gpu_tflops": tf_total / world,
+                "efficiency_vs_single_gpu_kernel": (full_ms / world) / t_ms,
+                "single_gpu_launch_ms": full_ms, "clocks": clk,
+                "note": "%d work items of 256 rows per GPU = %.2f waves of 148 SMs" % ((b1 - b0) * N // 256, (b1 - b0) * N / 256 / 148)}
+            if not args.no_e2e:
+                sub["strong_c3"]["e2e"] = e2e_arm(b0, b1, flops_of(B, H, N, d, causal))
+            del qs, ks, vs, os_, ls_
+        if world > 1:
+            # (ii) BASELINE configs[4]: c5 causal ring attention, one sequence over all ranks
+            del q, k, v, o, lse
+            torch.cuda.empty_cache()
+            sub["ring_c5"] = ring_record(torch, dist, fa, dev, rank, world, peaks, sub_steps, args.ring_transport, barrier,
+                                         max_over_ranks)
 
     # ---- CPU baseline beside it (rank 0, N == 1 only)
     cpu = None
@@ -351,10 +475,90 @@ def main():
                        "l2": ("inputs per step (%.0f MB) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e6))
                              if flush is None else "L2 flushed (512 MB write) between timed iterations"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "tmap_cache": dict(zip(("hits", "misses"), fa.tmap_cache_stats())),
         }
+        line.update(sub)
         print(json.dumps(line), flush=True)
     if world > 1:
+        fa.release_peer_buffers()
         dist.destroy_process_group()
+
+
+def ring_record(torch, dist, fa, dev, rank, world, peaks, steps, transport, barrier, max_over_ranks):
+    """c5 (BASELINE configs[4]) as a sub-record: causal ring attention of ONE 131072-token sequence over all ranks
+    (zig-zag partition), timed like the headline (CUDA events, barrier + sync both sides, max over ranks), plus -
+    outside the timed region - a parity check of the ring against a single-GPU attention_forward over the whole
+    sequence on one head, and a per-step timeline of one call."""
+    B, H, N, d, dtype_name, causal = WORKLOADS["c5"]
+    dtype = torch.bfloat16
+    n_local = N // world
+    q, k, v = synth(torch, (B, H, n_local, d), dtype, dev, 777 + rank)   # rank r's zig-zag rows [chunk r ; chunk 2P-1-r]
+
+    def step():
+        return fa.ring_attention(q, k, v, causal=causal, transport=transport)
+    for _ in range(3):
+        out, lse = step()
+    barrier()
+    smp = ClockSampler(dev); smp.start()
+    launches0 = fa.launch_count()
+    t_ms, per = timed_steps(torch, step, steps)
+    barrier()
+    launches = fa.launch_count() - launches0
+    clk = smp.stop()
+    t_ms = max_over_ranks(t_ms) / steps
+    fl = flops_of(B, H, N, d, causal)
+    per_gpu = fl / world / (t_ms * 1e-3) * 1e-12
+    rec = {"config": "BASELINE configs[4]: B=1 H=32 N=131072 d=128 bf16 causal, ring attention over %d GPUs (zig-zag)" % world,
+           "scaling": "strong", "n_gpus": world, "steps": steps, "ms_per_step": t_ms, "value": fl / (t_ms * 1e-3) * 1e-12,
+           "unit": UNIT, "per_gpu_tflops": per_gpu, "frac_of_measured_tensor_peak": per_gpu / peaks["tflops"],
+           "gpu_launches": int(launches), "clocks": clk}
+    ring = fa.c_ring_for(q, None) if transport != "p2p" else None
+    if ring is not None and ring.ok:
+        block = 2 * q.numel() * q.element_size()
+        rec["transport"] = ("C-ABI ring (fa_b200_ring_*): copy-engine pulls from the owner's CUDA-IPC buffer, two receive "
+                            "slots, ready/ack sequence flags (cuStreamWaitValue32), no collective in the step loop")
+        rec["handle_device_bytes"] = ring.device_bytes()
+        rec["handle_bytes_in_kv_blocks"] = ring.device_bytes() / block
+        rec["ring_traffic_bytes_per_rank_per_step"] = block
+        # one profiled call: where does a step's time go?
+        barrier()
+        ring.set_profile(True)
+        step()
+        torch.cuda.synchronize()
+        steps_tl, combine_done = ring.timeline()
+        ring.set_profile(False)
+        if rank == 0 and steps_tl:
+            wait = sum(r_ - b_ for (_, b_, r_, _) in steps_tl)
+            kern = sum(d_ - r_ for (_, _, r_, d_) in steps_tl)
+            rec["timeline_rank0_ms"] = {"steps": [{"step": s_, "begin": round(b_, 3), "kv_ready": round(r_, 3), "attn_done": round(d_, 3)}
+                                                  for (s_, b_, r_, d_) in steps_tl], "combine_done": combine_done,
+                                        "sum_wait_for_kv": wait, "sum_attention_kernels": kern,
+                                        "publish_and_flags_before_step0": steps_tl[0][1],
+                                        "combine": (combine_done - steps_tl[-1][3]) if combine_done else None}
+            parts = {"attention kernels": kern, "waiting for K/V blocks": wait, "publish": steps_tl[0][1],
+                     "combine": (combine_done - steps_tl[-1][3]) if combine_done else 0.0}
+            rec["limiter"] = max(parts, key=parts.get) + " (%.0f %% of the call)" % (100 * max(parts.values()) / max(combine_done or 1e-9, 1e-9))
+    else:
+        rec["transport"] = "NCCL send/recv (torch.distributed.batch_isend_irecv), all exchanges posted up front"
+    barrier()
+
+    # ---- parity, outside any timed region: head 0 of the ring result vs ONE attention_forward over the whole sequence
+    out, lse = step()
+    torch.cuda.synchronize()
+    gath = []
+    for t in (q[:, :1], k[:, :1], v[:, :1]):
+        parts = [torch.empty_like(t.contiguous()) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous())
+        gath.append(fa.zigzag_gather(parts))
+    o_one, lse_one = fa.attention_forward(gath[0], gath[1], gath[2], causal=True)
+    o_loc, lse_loc = fa.zigzag_split(o_one, world, rank), fa.zigzag_split(lse_one.unsqueeze(-1), world, rank).squeeze(-1)
+    err_o = float((out[:, :1].float() - o_loc.float()).abs().max())
+    err_l = float(((lse[:, :1] - lse_loc).abs() / lse_loc.abs().clamp(min=1.0)).max())
+    rec["parity_vs_single_gpu_head0"] = {"o_max_abs": max_over_ranks(err_o), "lse_max_rel": max_over_ranks(err_l),
+                                         "gate": "O 4e-3 (two bf16 roundings), lse 1e-4 relative",
+                                         "pass": bool(max_over_ranks(err_o) <= 4e-3 and max_over_ranks(err_l) <= 1e-4)}
+    barrier()
+    return rec
 
 
 if __name__ == "__main__":

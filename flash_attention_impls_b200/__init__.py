@@ -3,7 +3,7 @@
 The product is `lib/libfa_b200.so` (C ABI: include/fa_b200.h).  This package is the thin host-side
 mirror of the reference's operator interface plus the multi-GPU drivers ((b,h) sharding, ring attention).
 """
-from ._lib import FaB200Error, LIB_PATH, launch_count, load  # noqa: F401
+from ._lib import FaB200Error, LIB_PATH, launch_count, load, tmap_cache_stats  # noqa: F401
 from .ops import (  # noqa: F401
     FlashAttnFunction,
     HostPipeline,
@@ -22,6 +22,7 @@ from .ops import (  # noqa: F401
 )
 from .parallel import (  # noqa: F401
     bh_shard_range,
+    c_ring_for,
     release_peer_buffers,
     ring_attention,
     zigzag_gather,

@@ -26,8 +26,12 @@ EXPORTED_SYMBOLS = (
     "fa_b200_combine_partials", "fa_b200_cast_output", "fa_b200_backward", "fa_b200_host_ctx_create", "fa_b200_forward_host", "fa_b200_host_ctx_sync",
     "fa_b200_host_ctx_elapsed_ms", "fa_b200_host_ctx_destroy", "fa_b200_peer_alloc", "fa_b200_peer_free", "fa_b200_peer_open",
     "fa_b200_peer_close", "fa_b200_copy_async", "fa_b200_work_item", "fa_b200_launch_count", "fa_b200_last_error", "fa_b200_status_string",
-    "fa_b200_version",
+    "fa_b200_version", "fa_b200_tmap_cache_stats", "fa_b200_set_group_heads",
+    "fa_b200_ring_create", "fa_b200_ring_export", "fa_b200_ring_connect", "fa_b200_ring_forward", "fa_b200_ring_kv_buffers",
+    "fa_b200_ring_wait_consumed", "fa_b200_ring_device_bytes", "fa_b200_ring_set_profile", "fa_b200_ring_timeline",
+    "fa_b200_ring_destroy",
 )
+FA_B200_RING_EXPORT_BYTES = 128
 
 
 class FaB200Params(Structure):
@@ -125,6 +129,30 @@ def load() -> ctypes.CDLL:
     lib.fa_b200_status_string.restype = c_char_p
     lib.fa_b200_version.argtypes = []
     lib.fa_b200_version.restype = c_int
+    lib.fa_b200_set_group_heads.argtypes = [c_int]
+    lib.fa_b200_set_group_heads.restype = None
+    lib.fa_b200_tmap_cache_stats.argtypes = [POINTER(c_uint64), POINTER(c_uint64)]
+    lib.fa_b200_tmap_cache_stats.restype = None
+    lib.fa_b200_ring_create.argtypes = [c_int] * 7 + [POINTER(c_void_p)]
+    lib.fa_b200_ring_create.restype = c_int
+    lib.fa_b200_ring_export.argtypes = [c_void_p, ctypes.c_char_p]
+    lib.fa_b200_ring_export.restype = c_int
+    lib.fa_b200_ring_connect.argtypes = [c_void_p, ctypes.c_char_p]
+    lib.fa_b200_ring_connect.restype = c_int
+    lib.fa_b200_ring_forward.argtypes = [c_void_p] * 6 + [c_int, c_float, c_void_p]
+    lib.fa_b200_ring_forward.restype = c_int
+    lib.fa_b200_ring_kv_buffers.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]
+    lib.fa_b200_ring_kv_buffers.restype = c_int
+    lib.fa_b200_ring_wait_consumed.argtypes = [c_void_p, c_void_p]
+    lib.fa_b200_ring_wait_consumed.restype = c_int
+    lib.fa_b200_ring_device_bytes.argtypes = [c_void_p]
+    lib.fa_b200_ring_device_bytes.restype = ctypes.c_size_t
+    lib.fa_b200_ring_set_profile.argtypes = [c_void_p, c_int]
+    lib.fa_b200_ring_set_profile.restype = c_int
+    lib.fa_b200_ring_timeline.argtypes = [c_void_p, POINTER(c_float), c_int]
+    lib.fa_b200_ring_timeline.restype = c_int
+    lib.fa_b200_ring_destroy.argtypes = [c_void_p]
+    lib.fa_b200_ring_destroy.restype = c_int
     _lib = lib
     return lib
 
@@ -145,3 +173,10 @@ def work_item(B: int, H: int, N: int, d: int, causal: bool, index: int, N_kv: in
 
 def launch_count() -> int:
     return int(load().fa_b200_launch_count())
+
+
+def tmap_cache_stats():
+    """(hits, misses) of the library's TMA tensor-map cache."""
+    h, m = c_uint64(0), c_uint64(0)
+    load().fa_b200_tmap_cache_stats(ctypes.byref(h), ctypes.byref(m))
+    return int(h.value), int(m.value)

@@ -39,7 +39,8 @@ int fail(int code, const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
-  if (getenv("FA_B200_VERBOSE")) fprintf(stderr, "fa_b200: %s\n", g_err);
+  static const bool verbose = getenv("FA_B200_VERBOSE") != nullptr;   // read once per process
+  if (verbose) fprintf(stderr, "fa_b200: %s\n", g_err);
   return code;
 }
 
@@ -67,7 +68,7 @@ EncodeTiledFn get_encode_fn() {
 // batch (2) each outer axis carries, and the kernel orders its coordinates accordingly.  The box is
 // 64 columns x 128 rows x 1 x 1 with the 128-byte swizzle the UMMA descriptors expect (d = 32: 32 columns, 64-byte
 // swizzle).  Out-of-range rows read as zero and are clipped on store, which is what makes ragged N work.
-int make_tmap(CUtensorMap* tm, unsigned* perm, const void* base, int dtype, int d, long long rows, long long H,
+int encode_tmap(CUtensorMap* tm, unsigned* perm, const void* base, int dtype, int d, long long rows, long long H,
               long long B, long long sn, long long sh, long long sb) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
@@ -95,6 +96,46 @@ int make_tmap(CUtensorMap* tm, unsigned* perm, const void* base, int dtype, int 
                    d >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return FA_B200_OK;
+}
+
+// Tensor maps are pure functions of (pointer, shape, strides, dtype), and callers launch the same tensors over and
+// over (a training loop, the ring driver's recv slots, the host pipeline's staging buffers), so the encoded maps are
+// kept in a small per-thread cache: 32 entries, round-robin replacement, no locking.  A hit
+// costs a scan of at most 32 keys instead of a driver call; on a 67 us launch (BASELINE c2) four encodes are
+// measurable host time.  The map only holds address arithmetic, so a freed-and-reallocated buffer at the same
+// address with the same geometry is still described correctly.
+struct TmapKey {
+  const void* base;
+  long long rows, H, B, sn, sh, sb;
+  int dtype, d;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && H == o.H && B == o.B && sn == o.sn && sh == o.sh && sb == o.sb &&
+           dtype == o.dtype && d == o.d;
+  }
+};
+struct TmapEntry { TmapKey key; CUtensorMap map; unsigned perm; bool valid; };
+constexpr int kTmapCacheSize = 32;
+std::atomic<uint64_t> g_tmap_hits{0}, g_tmap_misses{0};
+
+int make_tmap(CUtensorMap* tm, unsigned* perm, const void* base, int dtype, int d, long long rows, long long H,
+              long long B, long long sn, long long sh, long long sb) {
+  thread_local TmapEntry cache[kTmapCacheSize] = {};
+  thread_local int next = 0;
+  const TmapKey key{base, rows, H, B, sn, sh, sb, dtype, d};
+  for (int i = 0; i < kTmapCacheSize; ++i)
+    if (cache[i].valid && cache[i].key == key) {
+      *tm = cache[i].map;
+      *perm = cache[i].perm;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return FA_B200_OK;
+    }
+  const int rc = encode_tmap(tm, perm, base, dtype, d, rows, H, B, sn, sh, sb);
+  if (rc) return rc;
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  TmapEntry& e = cache[next];
+  next = (next + 1) % kTmapCacheSize;
+  e.key = key; e.map = *tm; e.perm = *perm; e.valid = true;
   return FA_B200_OK;
 }
 
@@ -191,9 +232,25 @@ int launch_bwd(const CUtensorMap& f1, const CUtensorMap& f2, const CUtensorMap& 
   return FA_B200_OK;
 }
 
+// Bring-up overrides (UMMA descriptors, split count) exist only in -DFA_B200_DEBUG builds: a stray environment
+// variable must not be able to corrupt a descriptor in the shipped library.
+#ifdef FA_B200_DEBUG
 unsigned long long env_u64(const char* name, unsigned long long dflt) {
   const char* s = getenv(name);
   return s ? strtoull(s, nullptr, 0) : dflt;
+}
+#endif
+
+// FA_B200_GROUP_HEADS (tuning knob of the causal item order; 0 = the L2-sized default) is read once per process.
+std::atomic<long long> g_group_heads{-1};   // -1: not initialised yet
+long long group_heads_override() {
+  long long v = g_group_heads.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* s = getenv("FA_B200_GROUP_HEADS");
+    v = s ? std::max(0LL, strtoll(s, nullptr, 0)) : 0LL;
+    g_group_heads.store(v, std::memory_order_relaxed);
+  }
+  return v;
 }
 
 // Split-KV policy: how many key-axis splits for a launch with `items` work items of `n_kv_tiles` K/V tiles each.
@@ -202,7 +259,9 @@ int choose_nsplit(long long items, int n_kv_tiles, int sms) {
   long long n = sms / items;                                 // fill the machine once
   n = std::min<long long>(n, n_kv_tiles / 4);                // at least 4 tiles per split
   n = std::min<long long>(n, 32);
+#ifdef FA_B200_DEBUG
   n = (long long)env_u64("FA_B200_NSPLIT", (unsigned long long)n);
+#endif
   return (int)std::max<long long>(1, std::min<long long>(n, n_kv_tiles));
 }
 
@@ -210,14 +269,16 @@ size_t split_workspace_bytes(int nsplit, long long rows, int d) {
   return nsplit <= 1 ? 0 : (size_t)nsplit * rows * ((size_t)d * 2 + 2 * sizeof(float));
 }
 
+// SMs of the current device (queried once per device; 148 on B200, which is also the answer when no device is
+// visible - the host-only introspection calls must work on a CPU box).
 int sm_count() {
-  static std::atomic<int> cache{0};
-  int n = cache.load();
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int n = (dev < 64) ? cache[dev].load() : 0;
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;   // B200
-    cache.store(n);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev < 64) cache[dev].store(n);
   }
   return n;
 }
@@ -235,9 +296,8 @@ void fill_schedule(fa::FwdArgs& a, long long BH, int Nq, int Nkv, int d) {
   const long long kv_bytes_per_head = 4LL * Nkv * d;
   long long g = (64LL << 20) / (kv_bytes_per_head > 0 ? kv_bytes_per_head : 1);
   g = std::max<long long>(1, std::min<long long>(g, BH));
-  a.group_heads = (int)env_u64("FA_B200_GROUP_HEADS", (unsigned long long)g);
-  if (a.group_heads < 1) a.group_heads = 1;
-  if (a.group_heads > BH) a.group_heads = (int)BH;
+  if (group_heads_override() > 0) g = group_heads_override();
+  a.group_heads = (int)std::max<long long>(1, std::min<long long>(g, BH));
   a.nsplit = 1;
   a.tiles_per_split = (Nkv + fa::kBlockN - 1) / fa::kBlockN;
 }
@@ -374,11 +434,12 @@ int fa_b200_forward(const fa_b200_params* p) {
   }
   a.idesc_qk = fa::umma_idesc(fmt, 0, 0, 128, 128);
   a.idesc_pv = fa::umma_idesc(fmt, 0, 1, 128, (unsigned)d);
-  // bring-up overrides (debug only)
+#ifdef FA_B200_DEBUG   // bring-up overrides
   a.desc_hi_qk = env_u64("FA_B200_DESC_HI_QK", a.desc_hi_qk);
   a.desc_hi_v = env_u64("FA_B200_DESC_HI_V", a.desc_hi_v);
   a.idesc_qk = (unsigned)env_u64("FA_B200_IDESC_QK", a.idesc_qk);
   a.idesc_pv = (unsigned)env_u64("FA_B200_IDESC_PV", a.idesc_pv);
+#endif
 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
   // one CTA per work item; resident CTAs steal the not-yet-launched ones (cluster launch control), so the
@@ -495,7 +556,7 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
   {
     const long long rows = BH * p->N;
     const long long total = rows * (d / 8);
-    long long blocks = std::min<long long>((total + 255) / 256, 148LL * 8);
+    long long blocks = std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
     if (bf16)
       fa::bwd_delta_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)p->O, (const uint4*)p->dO, p->delta, rows, d);
     else
@@ -525,7 +586,12 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
   return rc;
 }
 
+void fa_b200_set_group_heads(int heads) { g_group_heads.store(heads > 0 ? heads : 0); }
 uint64_t fa_b200_launch_count(void) { return g_launches.load(); }
+void fa_b200_tmap_cache_stats(uint64_t* hits, uint64_t* misses) {
+  if (hits) *hits = g_tmap_hits.load();
+  if (misses) *misses = g_tmap_misses.load();
+}
 const char* fa_b200_last_error(void) { return g_err; }
 int fa_b200_version(void) { return (FA_B200_VERSION_MAJOR << 16) | FA_B200_VERSION_MINOR; }
 
@@ -551,4 +617,5 @@ namespace fa {
 void count_launch() { g_launches.fetch_add(1); }
 int api_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 int api_check_device() { return check_device(); }
+int api_sm_count() { return sm_count(); }
 }  // namespace fa

@@ -16,6 +16,7 @@ namespace fa {
 void count_launch();
 int api_fail(int code, const char* msg);
 int api_check_device();
+int api_sm_count();
 
 template <bool kBF16>
 __device__ __forceinline__ float2 unpack2(uint32_t u) {
@@ -157,7 +158,7 @@ int launch_split_combine(const void* O_part, const float* lse_part, const float*
 
 inline unsigned grid_for(long long work_items) {
   long long blocks = (work_items + 255) / 256;
-  const long long cap = 148LL * 8;   // 8 resident 256-thread CTAs per SM, 148 SMs
+  const long long cap = (long long)api_sm_count() * 8;   // 8 resident 256-thread CTAs per SM
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;

@@ -49,7 +49,8 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
     q: [B,H,N,d]; k, v: [B,H,N_kv,d]; fp16 or bf16.  Only the last dim has to be contiguous: batch, head and row
     strides are passed to the kernel's TMA descriptors as they are (multiples of 8 elements), so row sub-ranges of
     a longer sequence (what the ring driver passes) and `x.transpose(1, 2)` views of [B,N,H,d] tensors need no copy.
-    k and v must share their strides.  precise=True feeds P to the tensor cores as a hi+lo pair of 16-bit operands
+    k and v share their strides (else both are copied); views a TMA descriptor cannot address - a stride-0 broadcast such
+    as `k.expand(...)` for GQA, strides that are not multiples of 8 - are copied first.  precise=True feeds P to the tensor cores as a hi+lo pair of 16-bit operands
     (fp32-like P, the accuracy of the reference's CUDA-core FA1 kernel; about 1.4x the time) - see
     `fa_b200_params.precise` in include/fa_b200.h.
     """
@@ -64,15 +65,26 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
         raise TypeError("q, k, v must share a dtype")
     dtype = _dtype_code(q)
 
+    def tma_ok(t: torch.Tensor) -> bool:
+        # what a TMA descriptor can address: d contiguous, every other stride a positive multiple of 8 elements.
+        # Stride 0 (a broadcast view such as k.expand(B, H, N, d) for GQA/MQA) is NOT expressible: the C ABI
+        # reads 0 as "dense default", so such a view must never reach it as is.
+        return t.stride(3) == 1 and all(t.shape[i] == 1 or (t.stride(i) > 0 and t.stride(i) % 8 == 0) for i in range(3))
+
+    # inputs the descriptors cannot address are copied (broadcast heads, odd strides); outputs must be addressable
+    q, k, v = (t if tma_ok(t) else t.contiguous() for t in (q, k, v))
+
     def strides(t: torch.Tensor, what: str):
-        if t.stride(3) != 1:
-            raise ValueError(f"{what}: the last dimension must be contiguous; call .contiguous()")
+        if not tma_ok(t):
+            raise ValueError(f"{what}: needs a contiguous last dimension and batch/head/row strides that are positive "
+                             "multiples of 8 elements")
         # size-1 axes report arbitrary strides in torch: give the kernel the dense default (0) for those
         return tuple(t.stride(i) if t.shape[i] > 1 else 0 for i in range(3))
 
     qs, ks, vs = strides(q, "q"), strides(k, "k"), strides(v, "v")
-    if ks != vs:
-        raise ValueError("k and v must share their strides")
+    if ks != vs:      # K and V share one set of strides in the ABI
+        k, v = k.contiguous(), v.contiguous()
+        ks = vs = strides(k, "k")
     if out is None:
         out = torch.empty((B, H, N, d), dtype=q.dtype, device=q.device)
     if out.shape != (B, H, N, d) or out.dtype != q.dtype:
@@ -83,8 +95,9 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
     ss = None
     for s_ in (lse, l, m):
         if s_ is not None:
-            if s_.dtype != torch.float32 or s_.shape != (B, H, N) or (N > 1 and s_.stride(2) != 1):
-                raise ValueError("lse / l / m must be fp32 [B,H,N] with contiguous rows")
+            if s_.dtype != torch.float32 or s_.shape != (B, H, N) or (N > 1 and s_.stride(2) != 1) or \
+                    any(s_.shape[i] > 1 and s_.stride(i) <= 0 for i in range(2)):
+                raise ValueError("lse / l / m must be fp32 [B,H,N] with contiguous rows and positive strides")
             st = tuple(s_.stride(i) if s_.shape[i] > 1 else 0 for i in range(2))
             if ss is not None and st != ss:
                 raise ValueError("lse, l and m must share their strides")

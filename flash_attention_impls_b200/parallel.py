@@ -111,104 +111,100 @@ def _post_block_exchange(k, v, recv_k, recv_v, step, group, rank, world):
     return dist.batch_isend_irecv(ops_)
 
 
-class _PeerRing:
-    """K/V exchange over peer memory: CUDA-IPC buffers + copy-engine pulls (see include/fa_b200.h, peer section).
+class _CRing:
+    """`transport="peer"`: the ring driver behind the C ABI (`fa_b200_ring_*`, csrc/fa_ring.cu).
 
-    One instance per (block bytes, group, device), cached in `_peer_rings`.  Each rank owns two publish buffers
-    (K|V, double-buffered across calls) that every other rank of the node has mapped.  A call writes the local block
-    into publish buffer `n % 2`, runs one tiny all-reduce as the cross-rank "everything is published" barrier, then
-    pulls the P-1 remote blocks on a side stream, one event per block.  Because call n+1 uses the other buffer and
-    its barrier is stream-ordered after call n's compute, a buffer is only overwritten two calls later, when every
-    peer has finished pulling from it."""
+    One handle per (shard shape, dtype, group, device), cached in `_c_rings`.  Creation is the only place where the
+    ranks talk on the host: every rank creates its handle, and ONE all-gather carries (hostname, status, 128-byte
+    export blob), so that all ranks take the same decision - the peer transport is used only when every rank sits
+    on the same host and every create and every connect succeeded; otherwise every rank destroys its handle and the
+    group falls back to NCCL send/recv.  After that a forward is enqueue-only: copy-engine pulls through a window of
+    two receive slots, ordered by sequence flags in the mapped memory (no collective, no host synchronisation)."""
 
-    def __init__(self, block_bytes: int, group, device):
+    def __init__(self, shape, dtype, group, device):
         import ctypes
+        import socket
         from . import _lib
         self.lib, self.ct = _lib, ctypes
-        self.group, self.device, self.block_bytes = group, device, block_bytes
+        self.group, self.device = group, device
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.calls = 0
-        self.mine, handles = [], []
+        self.shape, self.dtype = tuple(shape), dtype
+        self.handle = ctypes.c_void_p()
+        self.ok = False
+        B, H, Nl, d = self.shape
+        code = _lib.FA_B200_BF16 if dtype == torch.bfloat16 else _lib.FA_B200_FP16
+        lib = _lib.load()
+        blob = ctypes.create_string_buffer(_lib.FA_B200_RING_EXPORT_BYTES)
         with torch.cuda.device(device):
-            for _ in range(2):
-                ptr = ctypes.c_void_p()
-                h = ctypes.create_string_buffer(64)
-                _lib.check(_lib.load().fa_b200_peer_alloc(2 * block_bytes, ctypes.byref(ptr), h))
-                self.mine.append(ptr.value)
-                handles.append(h.raw)
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, handles, group=group)
-            self.peers = []            # peers[r][buf] -> device pointer of rank r's publish buffer
-            for r, hs in enumerate(gathered):
-                if r == self.rank:
-                    self.peers.append(list(self.mine))
-                    continue
-                ptrs = []
-                for raw in hs:
-                    p_ = ctypes.c_void_p()
-                    _lib.check(_lib.load().fa_b200_peer_open(raw, ctypes.byref(p_)))
-                    ptrs.append(p_.value)
-                self.peers.append(ptrs)
-            self.copy_stream = torch.cuda.Stream(device)
-            self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+            st = lib.fa_b200_ring_create(self.world, self.rank, B, H, Nl, d, code, ctypes.byref(self.handle))
+            err = lib.fa_b200_last_error().decode() if st else ""
+            if st == 0:
+                st = lib.fa_b200_ring_export(self.handle, blob)
+            info = [None] * self.world
+            dist.all_gather_object(info, (socket.gethostname(), int(st), blob.raw, err), group=group)
+            good = all(i[1] == 0 for i in info) and len({i[0] for i in info}) == 1
+            st2 = -1
+            if good:
+                st2 = lib.fa_b200_ring_connect(self.handle, b"".join(i[2] for i in info))
+            flags = [None] * self.world
+            dist.all_gather_object(flags, int(st2), group=group)
+            self.ok = good and all(f == 0 for f in flags)
+            if not self.ok:
+                self.why = next((i[3] for i in info if i[1]), "") or ("ranks span several hosts" if len({i[0] for i in info}) > 1
+                                                                      else "fa_b200_ring_connect failed on a rank")
+                self.close()
 
-    def exchange(self, k, v, blocks):
-        """Publishes (k, v), then starts pulling blocks[s] <- rank (r - s) mod P for s = 1..P-1.
-        Returns one CUDA event per step (None for step 0)."""
-        lib, buf = self.lib.load(), self.calls % 2
-        self.calls += 1
-        cur = torch.cuda.current_stream(self.device)
-        nb = self.block_bytes
+    def forward(self, q, k, v, causal, softmax_scale=0.0):
+        out = torch.empty_like(q)
+        lse = torch.empty(q.shape[:3], dtype=torch.float32, device=q.device)
         with torch.cuda.device(self.device):
-            self.lib.check(lib.fa_b200_copy_async(self.mine[buf], k.data_ptr(), nb, cur.cuda_stream))
-            self.lib.check(lib.fa_b200_copy_async(self.mine[buf] + nb, v.data_ptr(), nb, cur.cuda_stream))
-            dist.all_reduce(self.flag, group=self.group)          # every rank's block is published
-            self.copy_stream.wait_stream(cur)
-            events = [None]
-            for s in range(1, self.world):
-                src = self.peers[(self.rank - s) % self.world][buf]
-                bk, bv = blocks[s]
-                self.lib.check(lib.fa_b200_copy_async(bk.data_ptr(), src, nb, self.copy_stream.cuda_stream))
-                self.lib.check(lib.fa_b200_copy_async(bv.data_ptr(), src + nb, nb, self.copy_stream.cuda_stream))
-                ev = torch.cuda.Event()
-                ev.record(self.copy_stream)
-                events.append(ev)
-        return events
+            self.lib.check(self.lib.load().fa_b200_ring_forward(
+                self.handle, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                1 if causal else 0, float(softmax_scale), torch.cuda.current_stream(self.device).cuda_stream))
+        return out, lse
 
+    def set_profile(self, on: bool):
+        self.lib.check(self.lib.load().fa_b200_ring_set_profile(self.handle, 1 if on else 0))
+
+    def timeline(self):
+        """[(step, begin_ms, kv_ready_ms, attn_done_ms), ...], combine_done_ms of the last (synchronised) forward."""
+        buf = (self.ct.c_float * (3 * self.world + 2))()
+        n = self.lib.load().fa_b200_ring_timeline(self.handle, buf, len(buf))
+        vals = [float(buf[i]) for i in range(max(n, 0))]
+        steps = [(s, vals[3 * s], vals[3 * s + 1], vals[3 * s + 2]) for s in range(self.world) if 3 * s + 2 < len(vals)]
+        return steps, (vals[-1] if vals else None)
+
+    def device_bytes(self) -> int:
+        return int(self.lib.load().fa_b200_ring_device_bytes(self.handle))
 
     def close(self):
-        """Unmaps the peers' buffers and frees this rank's publish buffers (collective: every rank must call it,
-        after a barrier, so that nobody is still pulling)."""
-        lib = self.lib.load()
-        with torch.cuda.device(self.device):
-            torch.cuda.synchronize(self.device)
-            for r, ptrs in enumerate(self.peers):
-                if r != self.rank:
-                    for p_ in ptrs:
-                        lib.fa_b200_peer_close(p_)
-            for p_ in self.mine:
-                lib.fa_b200_peer_free(p_)
-        self.peers, self.mine = [], []
+        """Collective in effect: no rank may still be pulling (callers synchronise the ranks first)."""
+        if self.handle:
+            with torch.cuda.device(self.device):
+                self.lib.load().fa_b200_ring_destroy(self.handle)
+            self.handle = self.ct.c_void_p()
 
 
-_peer_rings = {}
+_c_rings = {}
 
 
 def release_peer_buffers(group: Optional[dist.ProcessGroup] = None) -> None:
-    """Frees the CUDA-IPC publish buffers the "peer" transport caches per (block size, group, device).  Collective
+    """Destroys the ring handles the "peer" transport caches per (shard shape, dtype, group, device).  Collective
     over `group`; call it before destroying the process group if the buffers should not live until process exit."""
-    if not _peer_rings:
+    if not _c_rings:
         return
+    torch.cuda.synchronize()
     dist.barrier(group)
-    for key in [k for k in _peer_rings if k[1] == id(group)]:
-        _peer_rings.pop(key).close()
+    for key in [k for k in _c_rings if k[2] == id(group)]:
+        _c_rings.pop(key).close()
 
 
-def _peer_ring_for(k, group):
-    key = (k.numel() * k.element_size(), id(group), k.device.index)
-    ring = _peer_rings.get(key)
+def c_ring_for(q: torch.Tensor, group) -> "_CRing":
+    """The cached C-ABI ring handle for shards shaped like `q` (created collectively on first use)."""
+    key = (tuple(q.shape), q.dtype, id(group), q.device.index)
+    ring = _c_rings.get(key)
     if ring is None:
-        ring = _peer_rings[key] = _PeerRing(key[0], group, k.device)
+        ring = _c_rings[key] = _CRing(q.shape, q.dtype, group, q.device)
     return ring
 
 
@@ -222,11 +218,12 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     Returns (O_local `[B,H,N_local,d]` in q.dtype, lse_local `[B,H,N_local]` fp32).
 
     Step s (s = 0..P-1) works on the block owned by rank (r - s) mod P and leaves its partial in slot s; one
-    `combine_partials` pass merges the slots at the end; all P-1 remote blocks are requested up
-    front, so step s never waits on step s-1's transfer.  transport: "peer" = copy-engine pulls from CUDA-IPC
-    buffers (single node, no SM used), "p2p" = torch.distributed send/recv (NCCL or gloo), "auto" = "peer" for
-    CUDA tensors with the built-in backend, else "p2p".  With the zig-zag layout the causal structure per step
-    is one of
+    `combine_partials` pass merges the slots at the end.  transport: "peer" = the C-ABI ring (`fa_b200_ring_*`):
+    copy-engine pulls from the owner's CUDA-IPC buffer through a window of two receive slots, flag-ordered, no SM
+    used, everything preallocated in the handle (single node); "p2p" = torch.distributed send/recv (NCCL or gloo; all
+    P-1 exchanges posted up front); "auto" = "peer" for CUDA tensors with the built-in backend when every rank of
+    the group is on one host and can map its peers (decided collectively, once), else "p2p".  With the zig-zag
+    layout the causal structure per step is one of
       src == r : square causal on the local block
       src <  r : every local query row sees only the FIRST half of the visiting block (no mask)
       src >  r : only the SECOND half of the local query rows see the visiting block (no mask)
@@ -241,21 +238,26 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     if causal and Nl % 2:
         raise ValueError("causal ring attention needs an even local length (zig-zag halves)")
     half = Nl // 2
+    if transport not in ("auto", "peer", "p2p"):
+        raise ValueError("transport must be 'auto', 'peer' or 'p2p'")
+    if transport in ("auto", "peer") and backend is None and q.is_cuda and world > 1:
+        ring = c_ring_for(q, group)
+        if ring.ok:
+            return ring.forward(q.contiguous(), k.contiguous(), v.contiguous(), causal)
+        if transport == "peer":
+            raise RuntimeError(f"ring_attention(transport='peer') is not available for this group: {ring.why}")
+    elif transport == "peer" and world > 1:
+        raise ValueError("transport='peer' needs CUDA tensors and the built-in backend")
 
+    # ---- "p2p": NCCL / gloo send-recv schedule (also the host logic the CPU tests drive with the oracle backend)
     # slot s holds the partial of step s; a slot row that a step does not compute keeps lse = -inf and is skipped
     o_parts = torch.empty((world, B, H, Nl, d), dtype=q.dtype, device=q.device)
     lse_parts = torch.full((world, B, H, Nl), float("-inf"), dtype=torch.float32, device=q.device)
 
     own_k, own_v = k.contiguous(), v.contiguous()
     blocks = [(own_k, own_v)] + [(torch.empty_like(own_k), torch.empty_like(own_v)) for _ in range(world - 1)]
-    if transport == "auto":
-        transport = "peer" if (backend is None and q.is_cuda and world > 1) else "p2p"
-    if transport not in ("peer", "p2p"):
-        raise ValueError("transport must be 'auto', 'peer' or 'p2p'")
-    reqs, events = None, None
-    if world > 1 and transport == "peer":
-        events = _peer_ring_for(own_k, group).exchange(own_k, own_v, blocks)
-    elif world > 1:
+    reqs = None
+    if world > 1:
         reqs = [None] + [_post_block_exchange(own_k, own_v, blocks[s][0], blocks[s][1], s, group, rank, world)
                          for s in range(1, world)]
 
@@ -265,11 +267,8 @@ def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
         if prof:
             prof.mark(f"s{step}:begin")
         if step > 0:
-            if events is not None:
-                torch.cuda.current_stream(q.device).wait_event(events[step])
-            else:
-                for r_ in reqs[step]:
-                    r_.wait()
+            for r_ in reqs[step]:
+                r_.wait()
         if prof:
             prof.mark(f"s{step}:kv_ready")
         cur_k, cur_v = blocks[step]

@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define FA_B200_VERSION_MAJOR 0
-#define FA_B200_VERSION_MINOR 4
+#define FA_B200_VERSION_MINOR 5
 
 /* status codes (0 = ok).  The reference returns void and prints to stderr
  * (flash_attn_cutlass.cu:540-542, :510-514); the C ABI returns codes instead. */
@@ -194,6 +194,44 @@ int fa_b200_peer_open(const unsigned char handle[64], void** dev_ptr);
 int fa_b200_peer_close(void* dev_ptr);
 int fa_b200_copy_async(void* dst, const void* src, size_t bytes, void* stream);
 
+/* ---- ring attention behind the C ABI (SURVEY.md section 8b ownership row, 8e; BASELINE configs[4]) -----------------
+ * One handle per GPU (one process or host thread per GPU), single node.  The sequence is split over `world` ranks;
+ * rank r holds Q, K, V rows [B,H,n_local,d] (dense).  A forward runs `world` steps; step s attends the local queries
+ * to the K/V block of rank (r - s) mod world, which is PULLED from its owner's exported buffer by the copy engines
+ * (no SM, no NCCL kernel) through a window of two receive slots, ordered by 32-bit sequence flags in the mapped
+ * memory (4-byte DMA writes + cuStreamWaitValue32; no collective, no host synchronisation).  The partials are merged
+ * with their logsumexp.  Causal rings use the zig-zag partition: the local rows of rank r are sequence chunks r and
+ * 2*world-1-r (of 2*world equal chunks), in that order; non-causal rings accept any equal partition.
+ *
+ * Life cycle:  create (allocates everything the handle will ever use: one published K|V block, two receive slots,
+ * the partial stack - fa_b200_ring_device_bytes reports it; forward never allocates)  ->  export (a 128-byte blob)
+ * -> the CALLER exchanges the blobs between ranks by any means (MPI, torch.distributed, a file)  ->  connect (maps
+ * the peers; blobs in rank order)  ->  forward, any number of times, collectively (every rank the same number of
+ * calls)  ->  destroy (collective: no rank may still be pulling; synchronise the ranks first).
+ * Ranks living in the same process (one host thread per GPU) connect without IPC. */
+#define FA_B200_RING_EXPORT_BYTES 128
+typedef struct fa_b200_ring fa_b200_ring;
+int fa_b200_ring_create(int world, int rank, int B, int H, int n_local, int d, int dtype, fa_b200_ring** out);
+int fa_b200_ring_export(const fa_b200_ring* ring, unsigned char blob[FA_B200_RING_EXPORT_BYTES]);
+int fa_b200_ring_connect(fa_b200_ring* ring, const unsigned char* blobs /* world * FA_B200_RING_EXPORT_BYTES */);
+/* O [B,H,n_local,d] dtype and lse [B,H,n_local] fp32 (optional) for the local rows.  Enqueue-only on `stream` (plus the
+ * handle's own copy stream); softmax_scale 0 => 1/sqrt(d). */
+int fa_b200_ring_forward(fa_b200_ring* ring, const void* Q, const void* K, const void* V, void* O, float* lse,
+                         int causal, float softmax_scale, void* stream);
+/* Zero-copy publish: the handle's own K and V buffers (NULL for world == 1).  A caller that produces K/V straight
+ * into them and passes these pointers to forward() saves the publish copy; it must enqueue
+ * fa_b200_ring_wait_consumed on the producing stream first (the peers may still be pulling the previous block). */
+int fa_b200_ring_kv_buffers(fa_b200_ring* ring, void** k_buf, void** v_buf);
+int fa_b200_ring_wait_consumed(fa_b200_ring* ring, void* stream);
+/* Device memory the handle owns, in bytes (published block + two receive slots + partial stack + flags). */
+size_t fa_b200_ring_device_bytes(const fa_b200_ring* ring);
+/* Optional CUDA-event timeline of the most recent forward (diagnostics; costs a few event records per step):
+ * after set_profile(ring, 1) and a synchronised forward, timeline() writes milliseconds since the call started for
+ * [step0 begin, step0 K/V ready, step0 kernel done, step1 begin, ..., combine done] and returns the count (-1 on error). */
+int fa_b200_ring_set_profile(fa_b200_ring* ring, int on);
+int fa_b200_ring_timeline(fa_b200_ring* ring, float* ms, int cap);
+int fa_b200_ring_destroy(fa_b200_ring* ring);
+
 /* Introspection of the tile scheduler (host-only, no GPU needed): decodes work item `index` of the launch that
  * fa_b200_forward would make for this shape - which (b*H+h) slice, first query row, and how many 128-key K/V
  * tiles each of its two 128-row Q tiles visits (0 = tile skipped).  Returns the number of work items
@@ -202,8 +240,16 @@ int fa_b200_copy_async(void* dst, const void* src, size_t bytes, void* stream);
 int fa_b200_work_item(int B, int H, int N, int N_kv, int d, int causal, int index, int* bh, int* q0,
                       int* tiles0, int* tiles1);
 
+/* Tuning knob of the causal item order: heads per longest-first group (0 = the default, as many heads as keep
+ * their K/V in about half of the L2 together).  Process-wide; its initial value is read ONCE from the environment
+ * variable FA_B200_GROUP_HEADS.  Results never depend on it, only the order in which work items are visited. */
+void fa_b200_set_group_heads(int heads);
+
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t fa_b200_launch_count(void);
+
+/* Hits / misses of the per-thread TMA tensor-map cache (keyed on pointer, shape, strides, dtype). */
+void fa_b200_tmap_cache_stats(uint64_t* hits, uint64_t* misses);
 
 /* Message for the last non-OK status returned on the calling thread ("" if none). */
 const char* fa_b200_last_error(void);

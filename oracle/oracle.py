@@ -89,7 +89,7 @@ def attention_f64(q, k, v, causal=False, scale=None):
     return o, lse, l, m
 
 
-def attention_backward_f64(q, k, v, do, causal=False, scale=None):
+def attention_backward_f64(q, k, v, do, causal=False, scale=None, row_block=0):
     """Gradients of O = softmax(Q K^T scale [+ causal mask]) V w.r.t. Q, K, V for an upstream gradient dO, in numpy
     float64, per (b,h) slice to bound memory.  This is the mathematics the reference's Triton backward recomputes
     (FA2-triton.py:98-170: P from the saved row statistics, dV = P^T dO, dP = dO V^T, dS, dQ = dS K, dK = dS^T Q) with
@@ -99,6 +99,7 @@ def attention_backward_f64(q, k, v, do, causal=False, scale=None):
     (FA2-triton.py:158-159), which is not this Jacobian, and the reference never checks its backward (SURVEY.md section 4);
     the pin for this function is therefore torch.autograd through the reference's own `sdpa_reference`
     (tests/golden/make_golden_bwd.py -> tests/golden/sdpa_bwd_golden.npz).
+    `row_block` > 0 processes the query rows in blocks of that many rows (same result; bounds memory at long N).
     Returns (dQ, dK, dV, delta) as float64, delta[b,h,i] = dO_i . O_i."""
     q = np.asarray(q, np.float64); k = np.asarray(k, np.float64); v = np.asarray(v, np.float64)
     do = np.asarray(do, np.float64)
@@ -107,27 +108,28 @@ def attention_backward_f64(q, k, v, do, causal=False, scale=None):
     sc = scale if scale else 1.0 / math.sqrt(d)
     dq = np.zeros_like(q); dk = np.zeros_like(k); dv = np.zeros_like(v)
     delta = np.zeros((B, H, N))
-    if causal:
-        i = np.arange(N)[:, None]; j = np.arange(Nkv)[None, :]
-        masked = j > i + (Nkv - N)
+    rb = row_block if row_block else N          # query rows are independent: blocks of rows bound the N x Nkv temporaries
+    j = np.arange(Nkv)[None, :]
     for b in range(B):
         for h in range(H):
-            s = (q[b, h] @ k[b, h].T) * sc
-            if causal:
-                s = np.where(masked, -np.inf, s)
-            m = s.max(axis=-1, keepdims=True)
-            msafe = np.where(np.isfinite(m), m, 0.0)
-            e = np.exp(s - msafe)
-            l = e.sum(axis=-1, keepdims=True)
-            p = e / np.where(l > 0, l, 1.0)
-            o = p @ v[b, h]
-            dp = do[b, h] @ v[b, h].T
-            dl = (do[b, h] * o).sum(axis=-1, keepdims=True)
-            ds = p * (dp - dl) * sc
-            dq[b, h] = ds @ k[b, h]
-            dk[b, h] = ds.T @ q[b, h]
-            dv[b, h] = p.T @ do[b, h]
-            delta[b, h] = dl[:, 0]
+            for r0 in range(0, N, rb):
+                r1 = min(N, r0 + rb)
+                s = (q[b, h, r0:r1] @ k[b, h].T) * sc
+                if causal:
+                    s = np.where(j > np.arange(r0, r1)[:, None] + (Nkv - N), -np.inf, s)
+                m = s.max(axis=-1, keepdims=True)
+                msafe = np.where(np.isfinite(m), m, 0.0)
+                e = np.exp(s - msafe)
+                l = e.sum(axis=-1, keepdims=True)
+                p = e / np.where(l > 0, l, 1.0)
+                o = p @ v[b, h]
+                dp = do[b, h, r0:r1] @ v[b, h].T
+                dl = (do[b, h, r0:r1] * o).sum(axis=-1, keepdims=True)
+                ds = p * (dp - dl) * sc
+                dq[b, h, r0:r1] = ds @ k[b, h]
+                dk[b, h] += ds.T @ q[b, h, r0:r1]
+                dv[b, h] += p.T @ do[b, h, r0:r1]
+                delta[b, h, r0:r1] = dl[:, 0]
     return dq, dk, dv, delta
 
 

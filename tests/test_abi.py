@@ -48,7 +48,7 @@ def test_struct_layout_matches_header():
 
 def test_version_and_status_strings():
     lib = _lib.load()
-    assert lib.fa_b200_version() == (0 << 16) | 4
+    assert lib.fa_b200_version() == (0 << 16) | 5
     assert lib.fa_b200_status_string(0) == b"ok"
     assert lib.fa_b200_status_string(3) == b"unsupported head_dim"
     assert lib.fa_b200_status_string(99) == b"unknown status"
@@ -159,3 +159,29 @@ def test_workspace_query_policy():
     assert n > 0 and n % (8192 * (64 * 2 + 8)) == 0
     assert 2 <= n // (8192 * (64 * 2 + 8)) <= 32
     assert lib.fa_b200_workspace_bytes(1, 1, 8192, 0, 48) == 0            # invalid shape -> 0
+
+
+def test_ring_handle_validation_without_a_gpu():
+    """fa_b200_ring_* (SURVEY.md section 8b ownership row): argument errors are reported before any device call."""
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.fa_b200_ring_create(2, 0, 1, 1, 128, 64, 0, None) == 1
+    assert lib.fa_b200_ring_create(0, 0, 1, 1, 128, 64, 0, ctypes.byref(h)) == 2          # world
+    assert lib.fa_b200_ring_create(65, 0, 1, 1, 128, 64, 0, ctypes.byref(h)) == 2
+    assert lib.fa_b200_ring_create(2, 2, 1, 1, 128, 64, 0, ctypes.byref(h)) == 2          # rank
+    assert lib.fa_b200_ring_create(2, 0, 1, 1, 0, 64, 0, ctypes.byref(h)) == 2            # n_local
+    assert lib.fa_b200_ring_create(2, 0, 1, 1, 128, 48, 0, ctypes.byref(h)) == 3          # head_dim
+    assert lib.fa_b200_ring_create(2, 0, 1, 1, 128, 64, 5, ctypes.byref(h)) == 4          # dtype
+    assert not h.value
+    assert lib.fa_b200_ring_forward(None, None, None, None, None, None, 0, 0.0, None) == 1
+    assert lib.fa_b200_ring_export(None, None) == 1 and lib.fa_b200_ring_connect(None, None) == 1
+    assert lib.fa_b200_ring_device_bytes(None) == 0 and lib.fa_b200_ring_destroy(None) == 0
+    assert _lib.FA_B200_RING_EXPORT_BYTES == int(re.search(r"#define FA_B200_RING_EXPORT_BYTES (\d+)", open(HEADER).read()).group(1))
+
+
+def test_debug_overrides_are_compiled_out_of_the_release_library():
+    """The UMMA-descriptor / split-count environment overrides exist only in -DFA_B200_DEBUG builds."""
+    blob = open(_lib.LIB_PATH, "rb").read()
+    for name in (b"FA_B200_DESC_HI_QK", b"FA_B200_DESC_HI_V", b"FA_B200_IDESC_QK", b"FA_B200_IDESC_PV", b"FA_B200_NSPLIT"):
+        assert name not in blob, name
+    assert b"FA_B200_GROUP_HEADS" in blob      # the one tuning knob left, read once (and settable through the ABI)

@@ -113,11 +113,20 @@ def test_backward_is_deterministic_and_overwrites_its_outputs(fa):
     assert torch.isfinite(a[2].float()).all()
 
 
-def test_full_size_c4_backward_properties(fa):
-    """B=4 H=32 N=8192 d=128 bf16 causal (BASELINE c4's shape): sampled (b,h) slices against the oracle restricted to
-    the first 512 rows (causal: gradients of the first keys/queries depend on all later rows, so the check uses a
-    truncated problem: the first 512 rows of a causal problem form a causal problem of their own for dQ; dK/dV are
-    checked on a separate N=512 run), plus finiteness of the full result."""
+def _elementwise(got, ref, rtol, atol_rms):
+    """max over elements of |got - ref| / (rtol*|ref| + atol_rms*rms(ref)): <= 1 passes.  Element-wise, unlike `_rel`
+    (which is relative to the largest magnitude of the whole tensor)."""
+    got = got.float().cpu().numpy().astype(np.float64)
+    rms = float(np.sqrt(np.mean(ref * ref)))
+    return float((np.abs(got - ref) / (rtol * np.abs(ref) + atol_rms * rms)).max())
+
+
+def test_full_size_c4_backward_against_oracle(fa):
+    """B=4 H=32 N=8192 d=128 bf16 causal (BASELINE c4's shape).  One whole (b,h) slice - all 8192 rows of dQ, dK AND
+    dV - is checked against the float64 oracle (row-blocked, so it fits in memory) with an ELEMENT-WISE tolerance:
+    |err| <= 1e-2*|ref| + 1e-2*rms(ref) (a bf16 output alone carries 2^-8 = 3.9e-3 relative rounding; P and dS go to
+    the tensor cores as bf16).  A second slice gets the prefix check: dQ of the first 512 queries of a causal problem
+    only involves the first 512 keys.  Plus finiteness of the full result and bit-exact (b,h)-shard equivalence."""
     from oracle import oracle
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev); g.manual_seed(9)
@@ -131,12 +140,20 @@ def test_full_size_c4_backward_properties(fa):
     torch.cuda.synchronize()
     for t in (dq, dk, dv):
         assert torch.isfinite(t.float()).all()
-    # dQ of the first 512 queries only involves the first 512 keys (causal): compare with the oracle on that prefix
-    for (b, h) in ((0, 0), (3, 31)):
-        qs, ks, vs, dos = (t[b:b + 1, h:h + 1, :512].float().cpu().numpy() for t in (q, k, v, do))
-        rq, _, _, _ = oracle.attention_backward_f64(qs, ks, vs, dos, causal=True)
-        assert _rel(dq[b:b + 1, h:h + 1, :512], rq) <= TOL[torch.bfloat16]
-    # (b,h) shard equivalence: a slice computed alone is bit-identical
+    # (1) one full slice, every row, all three gradients
+    b, h = 3, 31
+    qs, ks, vs, dos = (t[b:b + 1, h:h + 1].float().cpu().numpy() for t in (q, k, v, do))
+    rq, rk, rv, _ = oracle.attention_backward_f64(qs, ks, vs, dos, causal=True, row_block=1024)
+    worst = {n_: _elementwise(got[b:b + 1, h:h + 1], ref, 1e-2, 1e-2) for n_, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv))}
+    rel = {n_: _rel(got[b:b + 1, h:h + 1], ref) for n_, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv))}
+    print("c4 backward vs oracle: element-wise ratio", worst, "relative-to-max", rel)
+    assert max(worst.values()) <= 1.0, (worst, rel)
+    assert max(rel.values()) <= TOL[torch.bfloat16]
+    # (2) prefix check on another slice
+    qs, ks, vs, dos = (t[0:1, 0:1, :512].float().cpu().numpy() for t in (q, k, v, do))
+    rq, _, _, _ = oracle.attention_backward_f64(qs, ks, vs, dos, causal=True)
+    assert _rel(dq[0:1, 0:1, :512], rq) <= TOL[torch.bfloat16]
+    # (3) (b,h) shard equivalence: a slice computed alone is bit-identical
     qs, ks, vs, dos, os_, ls_ = (t[1:2, 5:9].contiguous() for t in (q, k, v, do, o, lse))
     dq2, dk2, dv2 = fa.attention_backward(qs, ks, vs, os_, ls_, dos, causal=True)
     assert torch.equal(dq2, dq[1:2, 5:9]) and torch.equal(dk2, dk[1:2, 5:9]) and torch.equal(dv2, dv[1:2, 5:9])

@@ -50,10 +50,8 @@ def test_work_item_list_is_a_permutation_with_the_right_trip_counts(monkeypatch,
     trip counts that skip the K/V tiles above the causal diagonal, and - for causal launches - items ordered
     longest-first inside each group of heads."""
     from flash_attention_impls_b200 import _lib
-    if group is not None:
-        monkeypatch.setenv("FA_B200_GROUP_HEADS", group)
-    else:
-        monkeypatch.delenv("FA_B200_GROUP_HEADS", raising=False)
+    # the environment variable is only read once per process; the knob itself is a C-ABI call
+    _lib.load().fa_b200_set_group_heads(int(group) if group is not None else 0)
     nkv = Nkv or N
     n_items = _lib.work_item(B, H, N, d, causal, 0, Nkv)[0]
     nqb = (N + 255) // 256

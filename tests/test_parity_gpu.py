@@ -182,16 +182,19 @@ def test_large_score_range_exercises_lazy_rescale(fa):
     assert np.abs(m - m_ref).max() <= 1e-3 and (np.abs(l - l_ref) / l_ref).max() <= 1e-3
 
 
-def test_causal_head_group_order_does_not_change_results(fa, monkeypatch):
+def test_causal_head_group_order_does_not_change_results(fa):
     """Causal work items are ordered longest-first inside L2-sized groups of heads (get_item in the kernel header);
     any group size is just a permutation of the item list, so the outputs must be bit-identical."""
     q, k, v = _full_inputs(2, 24, 1100, 128, torch.bfloat16, seed=11)
     outs = []
-    for g in ("1", "5", "48", "1000"):
-        monkeypatch.setenv("FA_B200_GROUP_HEADS", g)
-        o, lse = fa.attention_forward(q, k, v, causal=True)
-        torch.cuda.synchronize()
-        outs.append((o.clone(), lse.clone()))
+    try:
+        for g in (1, 5, 48, 1000):
+            fa.load().fa_b200_set_group_heads(g)      # the C-ABI knob (the environment variable is read only once)
+            o, lse = fa.attention_forward(q, k, v, causal=True)
+            torch.cuda.synchronize()
+            outs.append((o.clone(), lse.clone()))
+    finally:
+        fa.load().fa_b200_set_group_heads(0)
     for o, lse in outs[1:]:
         assert torch.equal(o, outs[0][0]) and torch.equal(lse, outs[0][1])
 
@@ -546,3 +549,28 @@ def test_host_pipeline_e2e_matches_device_path(fa):
         pipe(hq, hk, hv, ho, hl)
     pipe.synchronize()
     assert torch.equal(ho, o.cpu()) and torch.equal(hl, lse.cpu())
+
+
+def test_broadcast_and_odd_stride_views_are_copied_not_misread(fa):
+    """A stride-0 view (GQA/MQA `k.expand(...)`) cannot be described to TMA, and the C ABI reads stride 0 as "dense
+    default": the Python surface must copy such inputs instead of letting the kernel read heads that do not exist.
+    Same for strides that are not multiples of 8 elements."""
+    from oracle import oracle
+    B, H, N, d = 2, 4, 320, 64
+    q, k1, v1 = oracle.set_s((B, H, N, d), (B, 1, N, d), seeds=(71, 72, 73))
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev, torch.bfloat16) for x in (q, k1, v1))
+    ke, ve = tk.expand(B, H, N, d), tv.expand(B, H, N, d)          # head stride 0
+    assert ke.stride(1) == 0
+    o, lse = fa.attention_forward(tq, ke, ve, causal=True)
+    torch.cuda.synchronize()
+    o_ref, lse_ref, _, _ = oracle.attention(q, np.broadcast_to(k1, (B, H, N, d)), np.broadcast_to(v1, (B, H, N, d)), causal=True)
+    _check(o.float().cpu().numpy(), lse.cpu().numpy(), o_ref, lse_ref)
+    # row stride d+4: not a multiple of 8 elements
+    wide = torch.zeros((B, H, N, d + 4), dtype=torch.bfloat16, device=dev)
+    wide[..., :d] = tq
+    o2, _ = fa.attention_forward(wide[..., :d], ke, ve, causal=True)
+    assert torch.equal(o2, o)
+    # an output the descriptors cannot address is an error, not a silent copy
+    with pytest.raises(ValueError):
+        fa.attention_forward(tq, ke, ve, out=torch.empty((B, 1, N, d), dtype=torch.bfloat16, device=dev).expand(B, H, N, d))

@@ -66,3 +66,45 @@ def test_ring_attention_nccl(causal, transport):
         lse = np.concatenate([r[2] for r in results], axis=2)
     assert np.abs(o - o_ref).max() <= 2e-3
     assert (np.abs(lse - lse_ref) / np.maximum(1.0, np.abs(lse_ref))).max() <= 1e-4
+
+
+# ------------------------------------------------------------------------------ the C-ABI ring (fa_b200_ring_*)
+@pytest.mark.parametrize("world,causal", [(2, True), (2, False), (4, True), (3, True)])
+def test_c_abi_ring_protocol_on_one_gpu(world, causal):
+    """world_size 2/3/4 of the C-ABI ring on ONE GPU (ranks in one process connect without IPC): ready/ack flags,
+    two-slot pull window, zig-zag schedule and combine, three back-to-back calls, against the oracle and against a
+    single attention_forward over the whole sequence.  Runs in a subprocess under a timeout so that a protocol bug
+    (a stream waiting on a flag forever) cannot hang the test session."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ring_emul.py"), str(world), str(int(causal)), "3"],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and r.stdout.strip().startswith("PASS"), r.stdout + r.stderr
+
+
+def test_c_abi_ring_world_one_and_argument_errors():
+    import ctypes
+    import flash_attention_impls_b200 as fa
+    from flash_attention_impls_b200 import _lib
+    from oracle import oracle
+    lib = fa.load()
+    dev = torch.device("cuda", 0)
+    h = ctypes.c_void_p()
+    _lib.check(lib.fa_b200_ring_create(1, 0, 1, 2, 300, 64, _lib.FA_B200_FP16, ctypes.byref(h)))
+    q, k, v = oracle.set_s((1, 2, 300, 64), (1, 2, 300, 64), seeds=(7, 8, 9))
+    tq, tk, tv = (torch.from_numpy(x).to(dev, torch.float16) for x in (q, k, v))
+    o = torch.empty_like(tq)
+    lse = torch.empty((1, 2, 300), dtype=torch.float32, device=dev)
+    _lib.check(lib.fa_b200_ring_forward(h, tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), o.data_ptr(), lse.data_ptr(), 1, 0.0,
+                                        torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v, causal=True)
+    assert np.abs(o.float().cpu().numpy() - o_ref).max() <= 2e-3
+    assert (np.abs(lse.cpu().numpy() - lse_ref) / np.maximum(1.0, np.abs(lse_ref))).max() <= 1e-4
+    assert lib.fa_b200_ring_device_bytes(h) == 0          # world 1 owns nothing
+    assert lib.fa_b200_ring_forward(h, None, tk.data_ptr(), tv.data_ptr(), o.data_ptr(), None, 0, 0.0, None) == 1   # ERR_NULL
+    lib.fa_b200_ring_destroy(h)
+    # a world-2 handle that has not been connected refuses to run
+    _lib.check(lib.fa_b200_ring_create(2, 1, 1, 2, 256, 64, _lib.FA_B200_FP16, ctypes.byref(h)))
+    assert lib.fa_b200_ring_forward(h, tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), o.data_ptr(), None, 0, 0.0, None) == 2
+    assert b"connect" in lib.fa_b200_last_error()
+    lib.fa_b200_ring_destroy(h)

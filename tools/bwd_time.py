@@ -12,16 +12,19 @@ sys.path.insert(0, ROOT)
 import flash_attention_impls_b200 as fa  # noqa: E402
 
 dev = torch.device("cuda:0")
-for (B, H, N, d, dtype, causal) in [(4, 32, 8192, 128, torch.bfloat16, False), (4, 32, 8192, 128, torch.bfloat16, True),
-                                    (8, 16, 1024, 64, torch.float16, False)]:
+SHAPES = [(4, 32, 8192, 128, torch.bfloat16, False), (4, 32, 8192, 128, torch.bfloat16, True),
+          (8, 16, 1024, 64, torch.float16, False)]
+if "--one" in sys.argv:          # short run for an ncu capture: the c3 shape on a quarter of the heads
+    SHAPES = [(1, 32, 8192, 128, torch.bfloat16, False)]
+for (B, H, N, d, dtype, causal) in SHAPES:
     g = torch.Generator(device=dev); g.manual_seed(1)
     q, k, v, do = (torch.randn((B, H, N, d), generator=g, device=dev).to(dtype) for _ in range(4))
     o, lse = fa.attention_forward(q, k, v, causal=causal)
-    for _ in range(3):
+    for _ in range(1 if "--one" in sys.argv else 3):
         fa.attention_backward(q, k, v, o, lse, do, causal=causal)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 10
+    n = 2 if "--one" in sys.argv else 10
     e0.record()
     for _ in range(n):
         fa.attention_backward(q, k, v, o, lse, do, causal=causal)
