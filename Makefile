@@ -28,3 +28,9 @@ clean:
 	rm -f $(PKG)/lib/*.so tools/fa_selftest; $(MAKE) -C oracle clean
 
 .PHONY: all lib oracle tools sass clean
+
+# library variants for interleaved A/B timing (tools/gpu_ab.sh): make variant NAME=p3 DEFS=-DFA_P_FIRST_Q=3
+variant:
+	mkdir -p build/$(NAME)
+	$(NVCC) $(NVFLAGS) $(DEFS) -shared -Xcompiler -fPIC -o build/$(NAME)/libfa_b200.so $(CSRC)
+.PHONY: variant

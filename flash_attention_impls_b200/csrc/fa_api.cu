@@ -232,6 +232,48 @@ int launch_bwd(const CUtensorMap& f1, const CUtensorMap& f2, const CUtensorMap& 
   return FA_B200_OK;
 }
 
+template <int D, bool kBF16, bool kCausal>
+int launch_bwd_dkdv(const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tq, const CUtensorMap& tdo,
+                    const CUtensorMap& tdk, const CUtensorMap& tdv, const fa::BwdArgs& args, long long grid, cudaStream_t stream) {
+  auto kern = fa::fa_bwd_dkdv_sm100_kernel<D, kBF16, kCausal>;
+  constexpr int smem = fa::BwdTraits<D>::kSmemBytes;
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load() & bit)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(bwd dkdv, smem=%d): %s", smem, cudaGetErrorString(e));
+    configured.fetch_or(bit);
+  }
+  kern<<<dim3((unsigned)grid), dim3(fa::kBwdDkdvThreads), smem, stream>>>(tk, tv, tq, tdo, tdk, tdv, args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "backward dK/dV kernel launch: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return FA_B200_OK;
+}
+
+template <int D, bool kBF16, bool kCausal>
+int launch_bwd_dq(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
+                  const CUtensorMap& tdq, const fa::BwdArgs& args, long long grid, cudaStream_t stream) {
+  auto kern = fa::fa_bwd_dq_sm100_kernel<D, kBF16, kCausal>;
+  constexpr int smem = fa::BwdTraits<D>::kSmemBytes;
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load() & bit)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(bwd dq, smem=%d): %s", smem, cudaGetErrorString(e));
+    configured.fetch_or(bit);
+  }
+  kern<<<dim3((unsigned)grid), dim3(fa::kBwdDkdvThreads), smem, stream>>>(tq, tdo, tk, tv, tdq, args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "backward dQ kernel launch: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return FA_B200_OK;
+}
+
 // Bring-up overrides (UMMA descriptors, split count) exist only in -DFA_B200_DEBUG builds: a stray environment
 // variable must not be able to corrupt a descriptor in the shipped library.
 #ifdef FA_B200_DEBUG
@@ -548,6 +590,7 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
   }
   a.idesc_ss = fa::umma_idesc(fmt, 0, 0, 128, 128);
   a.idesc_ts = fa::umma_idesc(fmt, 0, 1, 128, (unsigned)d);
+  a.idesc_ss_half = fa::umma_idesc(fmt, 0, 0, 128, 64);
 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(p->stream);
   const bool bf16 = p->dtype == FA_B200_BF16;
@@ -567,10 +610,20 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
   }
   const long long grid = BH * num_tiles;
   // 2. dQ kernel: fixed (Q, dO), streamed (K, V), out dQ;  3. dK/dV kernel: fixed (K, V), streamed (Q, dO), out dK (dS^T Q), dV
+#ifdef FA_BWD_DKDV_V1      // the one-tile-at-a-time dK/dV kernel of round 1 (kept for A/B measurements)
+#define FA_BWD_DKDV(D_, BF_, C_) launch_bwd<D_, BF_, C_, false>(tk, tv, tq, tdo, tdk, tdv, a, grid, stream)
+#else
+#define FA_BWD_DKDV(D_, BF_, C_) launch_bwd_dkdv<D_, BF_, C_>(tk, tv, tq, tdo, tdk, tdv, a, grid, stream)
+#endif
+#ifdef FA_BWD_DQ_V1        // the single-compute-warpgroup dQ kernel of round 1 (kept for A/B measurements)
+#define FA_BWD_DQ(D_, BF_, C_) launch_bwd<D_, BF_, C_, true>(tq, tdo, tk, tv, tdq, tdq, a, grid, stream)
+#else
+#define FA_BWD_DQ(D_, BF_, C_) launch_bwd_dq<D_, BF_, C_>(tq, tdo, tk, tv, tdq, a, grid, stream)
+#endif
 #define FA_BWD(D_, BF_, C_)                                                                 \
   do {                                                                                      \
-    rc = launch_bwd<D_, BF_, C_, true>(tq, tdo, tk, tv, tdq, tdq, a, grid, stream);         \
-    if (!rc) rc = launch_bwd<D_, BF_, C_, false>(tk, tv, tq, tdo, tdk, tdv, a, grid, stream); \
+    rc = FA_BWD_DQ(D_, BF_, C_);                                                            \
+    if (!rc) rc = FA_BWD_DKDV(D_, BF_, C_);                                                  \
   } while (0)
   if (d == 128) {
     if (bf16) { if (causal) FA_BWD(128, true, true); else FA_BWD(128, true, false); }
@@ -583,6 +636,8 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
     else      { if (causal) FA_BWD(64, false, true); else FA_BWD(64, false, false); }
   }
 #undef FA_BWD
+#undef FA_BWD_DKDV
+#undef FA_BWD_DQ
   return rc;
 }
 

@@ -151,6 +151,13 @@ __device__ __forceinline__ float2 ex2_emulated(float2 x) {
 #define FA_EMU_PAIRS_OF_4 0
 #endif
 
+// P is published to the MMA warp in two parts: the first FA_P_FIRST_Q groups of 32 keys, then the rest.  The part
+// that is published last sits on the softmax -> PV -> QK^T -> softmax chain: with 2 (halves) four PV MMAs (256 clk at
+// d = 128) follow the last arrival, with 3 only two (128 clk), at the price of a later start of the first burst.
+#ifndef FA_P_FIRST_Q
+#define FA_P_FIRST_Q 2
+#endif
+
 // Tensor maps are 4-D {d, a1, a2, a3}; `perm` says which of (row, head, batch) each outer axis carries.
 __device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int col, int row,
                                               int h, int b, unsigned int perm) {
@@ -411,8 +418,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         __syncwarp();
       };
-      // O_i += P_i V_j, issued in two halves of 64 keys: the first half starts as soon as the softmax
-      // warpgroup has published the first 64 columns of P, while it is still exponentiating the rest.
+      // O_i += P_i V_j, issued in two parts (FA_P_FIRST_Q groups of 32 keys, then the rest): the first part starts as
+      // soon as the softmax warpgroup has published those columns of P, while it is still exponentiating the rest.
       auto issue_pv = [&](int i, int stage, bool acc, uint32_t parity, uint32_t bar_done, uint32_t bar_release) {
         const uint32_t b_lo = lo_v | ((sKV + stage * kTileBytes) >> 4);
         const uint32_t p_tmem = tmem_base + i * kBlockN;           // P aliases S_i
@@ -423,11 +430,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_fence_after();
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 4 * h; k < 4 * h + 4; ++k)
+            for (int k = (h ? 2 * FA_P_FIRST_Q : 0); k < (h ? 8 : 2 * FA_P_FIRST_Q); ++k)
               umma_ts(d_tmem, p_tmem + k * 8, b_lo + k * (16 * kRowBytes / 16), hi_v, idesc_pv, (acc || k > 0) ? 1u : 0u);
             if constexpr (kPrecise) {   // O += P_lo V_j: the rounding residual of P, 64 columns further up
 #pragma unroll
-              for (int k = 4 * h; k < 4 * h + 4; ++k)
+              for (int k = (h ? 2 * FA_P_FIRST_Q : 0); k < (h ? 8 : 2 * FA_P_FIRST_Q); ++k)
                 umma_ts(d_tmem, p_tmem + kBlockN / 2 + k * 8, b_lo + k * (16 * kRowBytes / 16), hi_v, idesc_pv, 1u);
             }
             if (h == 1) {
@@ -706,11 +713,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           tmem_st16(tS + q * 16, pk);   // P(16-bit) over the first 64 columns of S
           if constexpr (kPrecise) tmem_st16(tS + kBlockN / 2 + q * 16, pl);   // P_lo over columns 64..127
-          if (q & 1) {
+          if (q == FA_P_FIRST_Q - 1 || q == 3) {
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(b_p_full + 8 * (q >> 1));
-            if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 2 + (q >> 1));
+            mbar_arrive(b_p_full + 8 * (q == 3 ? 1 : 0));
+            if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 2 + (q == 3 ? 1 : 0));
           }
         }
         const float2 lsum = __fadd2_rn(__fadd2_rn(lsum2[0], lsum2[1]), __fadd2_rn(lsum2[2], lsum2[3]));

@@ -64,6 +64,24 @@ def main():
             ql, kl, vl = shards[r]
             _lib.check(lib.fa_b200_ring_forward(rings[r], ql.data_ptr(), kl.data_ptr(), vl.data_ptr(), outs[r].data_ptr(),
                                                 lses[r].data_ptr(), 1 if causal else 0, 0.0, streams[r].cuda_stream))
+        # never block on a device-side wait that might not be satisfied: poll the streams with a deadline and, if they
+        # do not drain, dump the sequence flags (which rank is waiting for whom) before giving up
+        import time
+        deadline = time.time() + 30.0
+        while not all(s_.query() for s_ in streams) and time.time() < deadline:
+            time.sleep(0.01)
+        if not all(s_.query() for s_ in streams):
+            side = torch.cuda.Stream(dev)
+            dump = torch.zeros(128, dtype=torch.int32, device=dev)
+            for r in range(world):
+                kb, vb = ctypes.c_void_p(), ctypes.c_void_p()
+                lib.fa_b200_ring_kv_buffers(rings[r], ctypes.byref(kb), ctypes.byref(vb))
+                lib.fa_b200_copy_async(dump.data_ptr(), kb.value + 2 * block, 512, side.cuda_stream)
+                side.synchronize()
+                fl = dump.cpu().tolist()
+                print(f"STUCK call={call} rank={r} stream_done={streams[r].query()} ready={fl[:world]} ack={fl[64:64 + world]}", flush=True)
+            print(f"FAIL world={world} causal={int(causal)}: streams did not drain within 30 s", flush=True)
+            os._exit(1)
         torch.cuda.synchronize()
         if causal:
             o, lse = zigzag_gather(outs), zigzag_gather(lses)

@@ -77,7 +77,7 @@ def test_c_abi_ring_protocol_on_one_gpu(world, causal):
     (a stream waiting on a flag forever) cannot hang the test session."""
     import subprocess
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ring_emul.py"), str(world), str(int(causal)), "3"],
-                       capture_output=True, text=True, timeout=240)
+                       capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip().startswith("PASS"), r.stdout + r.stderr
 
 
