@@ -249,6 +249,29 @@ def kernel_record(torch, fa, name, dev, peaks, steps):
             "l2": "L2 flushed (512 MB write) between timed iterations" if flush is not None else "inputs exceed L2"}
 
 
+def backward_record(torch, fa, dev, peaks, steps):
+    """SURVEY.md section 8f.4 as a sub-record: fa_b200_backward (delta pre-pass + dQ kernel + dK/dV kernel) at the c3 shape.
+    FLOPs in the usual 5-product convention, 10*B*H*N^2*d (the two kernels execute 7 products: S and dP are recomputed)."""
+    B, H, N, d, dtype_name, causal = WORKLOADS["c3"]
+    q, k, v = synth(torch, (B, H, N, d), torch.bfloat16, dev, 99)
+    do = torch.randn_like(q)
+    o, lse = fa.attention_forward(q, k, v, causal=causal)
+
+    def step():
+        fa.attention_backward(q, k, v, o, lse, do, causal=causal)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    launches0 = fa.launch_count()
+    total, per = timed_steps(torch, step, steps)
+    ms = total / steps
+    tf = 10.0 * B * H * N * N * d / (ms * 1e-3) * 1e-12
+    return {"workload": "backward at the c3 shape (B=4 H=32 N=8192 d=128 bf16 non-causal)", "steps": steps, "ms_per_step": ms,
+            "tflops_5_product_convention": tf, "frac_of_measured_tensor_peak": tf / peaks["tflops"],
+            "tflops_as_executed_7_products": tf * 1.4, "gpu_launches": int(fa.launch_count() - launches0),
+            "kernels": "bwd_delta_kernel, fa_bwd_dq_sm100_kernel, fa_bwd_dkdv_sm100_kernel"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -415,6 +438,7 @@ def main():
         if world == 1:
             for name in ("c2", "c4"):
                 sub[name] = kernel_record(torch, fa, name, dev, peaks, max(sub_steps, 20))
+            sub["backward_c3"] = backward_record(torch, fa, dev, peaks, sub_steps)
         else:
             # (i) BASELINE configs[2]: c3 (batch,head)-SHARDED over the ranks - strong scaling, no collective
             b0, b1 = fa.bh_shard_range(B * H, world, rank)

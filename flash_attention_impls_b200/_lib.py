@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "fa_b200_ring_wait_consumed", "fa_b200_ring_device_bytes", "fa_b200_ring_set_profile", "fa_b200_ring_timeline",
     "fa_b200_ring_destroy",
 )
-FA_B200_RING_EXPORT_BYTES = 128
+FA_B200_RING_EXPORT_BYTES = 512
 
 
 class FaB200Params(Structure):

@@ -236,7 +236,7 @@ template <int D, bool kBF16, bool kCausal>
 int launch_bwd_dkdv(const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tq, const CUtensorMap& tdo,
                     const CUtensorMap& tdk, const CUtensorMap& tdv, const fa::BwdArgs& args, long long grid, cudaStream_t stream) {
   auto kern = fa::fa_bwd_dkdv_sm100_kernel<D, kBF16, kCausal>;
-  constexpr int smem = fa::BwdTraits<D>::kSmemBytes;
+  constexpr int smem = fa::BwdTraits<D>::kSmem2Bytes;
   static std::atomic<unsigned long long> configured{0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -257,7 +257,7 @@ template <int D, bool kBF16, bool kCausal>
 int launch_bwd_dq(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
                   const CUtensorMap& tdq, const fa::BwdArgs& args, long long grid, cudaStream_t stream) {
   auto kern = fa::fa_bwd_dq_sm100_kernel<D, kBF16, kCausal>;
-  constexpr int smem = fa::BwdTraits<D>::kSmemBytes;
+  constexpr int smem = fa::BwdTraits<D>::kSmem2Bytes;
   static std::atomic<unsigned long long> configured{0};
   int dev = 0;
   cudaGetDevice(&dev);

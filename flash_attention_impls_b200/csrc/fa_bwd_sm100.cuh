@@ -52,7 +52,19 @@ struct BwdTraits {
   using F = FwdTraits<D>;
   static constexpr int kTileBytes = F::kTileBytes;
   static constexpr int kAuxBytes = 4096;   // barriers (256 B) + column statistics 2 stages x 2 x 512 B
-  static constexpr int kSmemBytes = 6 * kTileBytes + kAuxBytes;   // F1 F2 | 2 stages x (T1 T2) | aux
+  static constexpr int kSmemBytes = 6 * kTileBytes + kAuxBytes;   // F1 F2 | 2 stages x (T1 T2) | aux   (round-1 kernel)
+  // Round-2 kernels: the streamed tiles go through a ring of single-tile SLOTS (tile t of the stream, two per step, sits
+  // in slot t % kSlots with its own full / empty barrier), as many as fit beside the two fixed tiles: 5 at d = 128
+  // (7 x 32 KB + 3 KB = the 227 KB opt-in maximum), 8 below.  With 2 pair-stages the load of step n+2 could only start
+  // when step n had completely finished and was needed at once: its whole latency sat on every step (ncu r02: the MMA
+  // warp spins on the "tile landed" barrier, the tensor pipe is 48 % active whatever the compute warps do).  With 5
+  // slots the slot of the first tile of step n+2 is already free during step n, and the second one as soon as the
+  // first product that reads it has completed (dQ kernel: V_j is only read by dP = dO V^T).
+  static constexpr int kAux2Bytes = 3072;  // barriers (256 B) + column statistics (2 KB)
+  static constexpr int kSlotsMax = (kSmemLimit - kAux2Bytes - 2 * kTileBytes) / kTileBytes;
+  static constexpr int kSlots = kSlotsMax > 8 ? 8 : kSlotsMax;
+  static constexpr int kSmem2Bytes = (2 + kSlots) * kTileBytes + kAux2Bytes;
+  static_assert(kSlots >= 5, "slot ring too shallow");
 };
 
 // delta[row] = sum_t dO[row,t] * O[row,t]  (fp32).  One thread per 8 elements, d/8 lanes per row.
@@ -454,15 +466,18 @@ fa_bwd_dkdv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();
   const uint32_t sK = smem_base, sV = smem_base + kTileBytes;
-  const uint32_t sT = smem_base + 2 * kTileBytes;             // stage s: Q_i at sT + 2 s tile, dO_i one tile further
-  const uint32_t bars = smem_base + 6 * kTileBytes;
+  constexpr int kSlots = BwdTraits<D>::kSlots;
+  const uint32_t sT = smem_base + 2 * kTileBytes;             // slot ring: stream tile t (Q_i: t = 2 n, dO_i: t = 2 n + 1)
+  const uint32_t bars = smem_base + (2 + kSlots) * kTileBytes;
   const uint32_t bar_f_full = bars;            //      TMA -> MMA  (K_j, V_j)
-  const uint32_t bar_t_full = bars + 8;        // [2]  TMA -> MMA  (Q_i, dO_i)
-  const uint32_t bar_t_empty = bars + 24;      // [2]  MMA -> TMA
-  const uint32_t bar_s_full = bars + 40;       // [2 halves]  MMA -> compute (S_h and dP_h are in TMEM)
-  const uint32_t bar_p_full = bars + 56;       // [2 halves]  compute -> MMA (P_h and dS_h are in TMEM; 128 arrivals)
-  const uint32_t bar_acc_full = bars + 72;     //      MMA -> compute (all accumulating products have landed)
-  const uint32_t tmem_slot = bars + 80;
+  const uint32_t bar_t_full = bars + 8;        // [kSlots]  TMA -> MMA  (a streamed tile has landed)
+  const uint32_t bar_t_empty = bars + 72;      // [kSlots]  MMA -> TMA  (every product reading the slot has completed)
+  const uint32_t bar_s_full = bars + 136;      // [2 halves]  MMA -> compute (S_h and dP_h are in TMEM)
+  const uint32_t bar_p_full = bars + 152;      // [2 halves]  compute -> MMA (P_h and dS_h are in TMEM; 128 arrivals)
+  const uint32_t bar_acc_full = bars + 168;    //      MMA -> compute (all accumulating products have landed)
+  const uint32_t tmem_slot = bars + 176;
+  auto slot_of = [&](int t) { return uint32_t(t % kSlots); };
+  auto phase_of = [&](int t) { return uint32_t((t / kSlots) & 1); };
   const uint32_t s_stats = bars + 256;         // [2 halves][2 stages][lse2(64) | delta(64)] fp32 = 2 KB
 
   const int warp = threadIdx.x >> 5;
@@ -479,9 +494,11 @@ fa_bwd_dkdv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
   }
   if (warp == 9 && lane == 0) {
     mbar_init(bar_f_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
       mbar_init(bar_t_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar_s_full + 8 * s, 1);
       mbar_init(bar_p_full + 8 * s, 128);
     }
@@ -510,12 +527,11 @@ fa_bwd_dkdv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
       mbar_arrive_expect_tx(bar_f_full, 2 * kTileBytes);
       load_tile(&tmK, sK, bar_f_full, f * kBlockM);
       load_tile(&tmV, sV, bar_f_full, f * kBlockM);
-      for (int n = 0; n < steps; ++n) {
-        const int s = n & 1;
-        mbar_wait(bar_t_empty + 8 * s, (uint32_t(n >> 1) & 1u) ^ 1u, 500 + s);
-        mbar_arrive_expect_tx(bar_t_full + 8 * s, 2 * kTileBytes);
-        load_tile(&tmQ, sT + (2 * s) * kTileBytes, bar_t_full + 8 * s, (t_begin + n) * kBlockN);
-        load_tile(&tmdO, sT + (2 * s + 1) * kTileBytes, bar_t_full + 8 * s, (t_begin + n) * kBlockN);
+      for (int t = 0; t < 2 * steps; ++t) {
+        const uint32_t s = slot_of(t);
+        mbar_wait(bar_t_empty + 8 * s, phase_of(t) ^ 1u, 500);
+        mbar_arrive_expect_tx(bar_t_full + 8 * s, kTileBytes);
+        load_tile((t & 1) ? &tmdO : &tmQ, sT + s * kTileBytes, bar_t_full + 8 * s, (t_begin + (t >> 1)) * kBlockN);
       }
     }
     __syncwarp();
@@ -555,28 +571,34 @@ fa_bwd_dkdv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
         umma_ts(tdV, tP + k * 8, bdO + (4 * h + k) * (16 * kRowBytes / 16), hi_mn, a.idesc_ts, (acc || k > 0) ? 1u : 0u);
     };
     mbar_wait(bar_f_full, 0, 600);
-    mbar_wait(bar_t_full, 0, 610);
+    mbar_wait(bar_t_full + 8 * slot_of(0), phase_of(0), 610);
+    mbar_wait(bar_t_full + 8 * slot_of(1), phase_of(1), 611);
     tc_fence_after();
     if (elect_one_sync()) {
-      issue_scores(0, sT, sT + kTileBytes);
+      issue_scores(0, sT + slot_of(0) * kTileBytes, sT + slot_of(1) * kTileBytes);
       umma_commit(bar_s_full);
-      issue_scores(1, sT, sT + kTileBytes);
+      issue_scores(1, sT + slot_of(0) * kTileBytes, sT + slot_of(1) * kTileBytes);
       umma_commit(bar_s_full + 8);
     }
     __syncwarp();
     for (int n = 0; n < steps; ++n) {
-      const int s = n & 1, s1 = (n + 1) & 1;
-      const uint32_t sQ = sT + (2 * s) * kTileBytes, sdO = sQ + kTileBytes;
-      const uint32_t sQ1 = sT + (2 * s1) * kTileBytes, sdO1 = sQ1 + kTileBytes;
+      const uint32_t sQ = sT + slot_of(2 * n) * kTileBytes, sdO = sT + slot_of(2 * n + 1) * kTileBytes;
+      const uint32_t sQ1 = sT + slot_of(2 * n + 2) * kTileBytes, sdO1 = sT + slot_of(2 * n + 3) * kTileBytes;
       const bool more = n + 1 < steps;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         mbar_wait(bar_p_full + 8 * h, uint32_t(n) & 1u, 620 + h);
-        if (h == 0 && more) mbar_wait(bar_t_full + 8 * s1, uint32_t((n + 1) >> 1) & 1u, 612 + s1);
+        if (h == 0 && more) {
+          mbar_wait(bar_t_full + 8 * slot_of(2 * n + 2), phase_of(2 * n + 2), 612);
+          mbar_wait(bar_t_full + 8 * slot_of(2 * n + 3), phase_of(2 * n + 3), 613);
+        }
         tc_fence_after();
         if (elect_one_sync()) {
           issue_acc(h, sQ, sdO, n > 0 || h > 0);
-          if (h == 1) umma_commit(bar_t_empty + 8 * s);          // every read of stage s has been issued
+          if (h == 1) {                                          // every read of Q_i and dO_i has been issued
+            umma_commit(bar_t_empty + 8 * slot_of(2 * n));
+            umma_commit(bar_t_empty + 8 * slot_of(2 * n + 1));
+          }
           if (more) {
             issue_scores(h, sQ1, sdO1);
             umma_commit(bar_s_full + 8 * h);
@@ -597,18 +619,20 @@ fa_bwd_dkdv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
     const int key_idx = f * kBlockM + row_in_tile;
     const long long stat_base = (long long)bh * a.N;
     const float log2e = 1.4426950408889634f;
+    // column statistics of this half's 64 queries of tile t: threads 0..63 fetch lse * log2e, threads 64..127 delta.
+    // The global load for step n+1 is issued during step n, so its latency is not on the step's critical chain.
+    auto fetch_stat = [&](int t) -> float {
+      const int qi = t * kBlockN + h * kHalf + (row_in_tile & (kHalf - 1));
+      if (row_in_tile < kHalf) return qi < a.N ? a.lse[stat_base + qi] * log2e : INFINITY;
+      return qi < a.N ? a.delta[stat_base + qi] : 0.f;
+    };
+    float stat_next = fetch_stat(t_begin);
     for (int n = 0; n < steps; ++n) {
       const int t = t_begin + n;
       const uint32_t st = s_stats + uint32_t(h) * 1024u + uint32_t(n & 1) * 512u;
-      {  // column statistics of this half's 64 queries: threads 0..63 publish lse * log2e, threads 64..127 delta
-        const int c = row_in_tile & (kHalf - 1);
-        const int qi = t * kBlockN + h * kHalf + c;
-        float val;
-        if (row_in_tile < kHalf) val = qi < a.N ? a.lse[stat_base + qi] * log2e : INFINITY;
-        else val = qi < a.N ? a.delta[stat_base + qi] : 0.f;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(st + uint32_t(row_in_tile) * 4u), "f"(val) : "memory");
-        named_bar_sync(1 + h, 128);
-      }
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(st + uint32_t(row_in_tile) * 4u), "f"(stat_next) : "memory");
+      named_bar_sync(1 + h, 128);
+      if (n + 1 < steps) stat_next = fetch_stat(t + 1);
       // visible query columns of this key row inside the half: c >= c_lo (causal: query >= key); keys beyond N see nothing
       int c_lo = 0;
       if (kCausal) c_lo = max(0, key_idx - t * kBlockN - h * kHalf);
@@ -730,16 +754,21 @@ fa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();
   const uint32_t sQ = smem_base, sdO = smem_base + kTileBytes;
-  const uint32_t sT = smem_base + 2 * kTileBytes;             // stage s: K_j at sT + 2 s tile, V_j one tile further
-  const uint32_t bars = smem_base + 6 * kTileBytes;
+  constexpr int kSlots = BwdTraits<D>::kSlots;
+  const uint32_t sT = smem_base + 2 * kTileBytes;             // slot ring: stream tile t (V_j: t = 2 n, K_j: t = 2 n + 1)
+  const uint32_t bars = smem_base + (2 + kSlots) * kTileBytes;
   const uint32_t bar_f_full = bars;            //      TMA -> MMA  (Q_i, dO_i)
-  const uint32_t bar_t_full = bars + 8;        // [2]  TMA -> MMA  (K_j, V_j)
-  const uint32_t bar_t_empty = bars + 24;      // [2]  MMA -> TMA
-  const uint32_t bar_s_full = bars + 40;       //      MMA -> compute (S and dP are in TMEM)
-  const uint32_t bar_p_full = bars + 48;       //      compute -> MMA (dS is in TMEM; 256 arrivals)
-  const uint32_t bar_acc_full = bars + 56;     //      MMA -> compute (dQ complete)
-  const uint32_t bar_s_free = bars + 64;       //      compute -> MMA (S is in registers; 256 arrivals)
-  const uint32_t tmem_slot = bars + 80;
+  const uint32_t bar_t_full = bars + 8;        // [kSlots]  TMA -> MMA  (a streamed tile has landed)
+  const uint32_t bar_t_empty = bars + 72;      // [kSlots]  MMA -> TMA  (every product reading the slot has completed)
+  const uint32_t bar_s_full = bars + 136;      //      MMA -> compute (S and dP are in TMEM)
+  const uint32_t bar_p_full = bars + 144;      //      compute -> MMA (dS is in TMEM; 256 arrivals)
+  const uint32_t bar_acc_full = bars + 152;    //      MMA -> compute (dQ complete)
+  const uint32_t bar_s_free = bars + 160;      //      compute -> MMA (S is in registers; 256 arrivals)
+  const uint32_t tmem_slot = bars + 176;
+  // V_j goes first in the stream: its slot is released as soon as dP = dO V^T has completed (early in the step), and
+  // with 5 slots that is the slot K_{j+2} lands in, while V_{j+2} takes the slot K_{j-1} gave up a step earlier
+  auto slot_of = [&](int t) { return uint32_t(t % kSlots); };
+  auto phase_of = [&](int t) { return uint32_t((t / kSlots) & 1); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -754,7 +783,7 @@ fa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
   if (warp == 9 && lane == 0) {
     mbar_init(bar_f_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
       mbar_init(bar_t_empty + 8 * s, 1);
     }
@@ -788,12 +817,11 @@ fa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_arrive_expect_tx(bar_f_full, 2 * kTileBytes);
       load_tile(&tmQ, sQ, bar_f_full, f * kBlockM);
       load_tile(&tmdO, sdO, bar_f_full, f * kBlockM);
-      for (int n = 0; n < steps; ++n) {
-        const int s = n & 1;
-        mbar_wait(bar_t_empty + 8 * s, (uint32_t(n >> 1) & 1u) ^ 1u, 500 + s);
-        mbar_arrive_expect_tx(bar_t_full + 8 * s, 2 * kTileBytes);
-        load_tile(&tmK, sT + (2 * s) * kTileBytes, bar_t_full + 8 * s, n * kBlockN);
-        load_tile(&tmV, sT + (2 * s + 1) * kTileBytes, bar_t_full + 8 * s, n * kBlockN);
+      for (int t = 0; t < 2 * steps; ++t) {
+        const uint32_t s = slot_of(t);
+        mbar_wait(bar_t_empty + 8 * s, phase_of(t) ^ 1u, 500);
+        mbar_arrive_expect_tx(bar_t_full + 8 * s, kTileBytes);
+        load_tile((t & 1) ? &tmK : &tmV, sT + s * kTileBytes, bar_t_full + 8 * s, (t >> 1) * kBlockN);
       }
     }
     __syncwarp();
@@ -810,41 +838,40 @@ fa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         umma_ss(d_tmem, a_lo + off, hi_k, b_lo + off, hi_k, a.idesc_ss, k > 0 ? 1u : 0u);
       }
     };
-    mbar_wait(bar_f_full, 0, 600);
-    mbar_wait(bar_t_full, 0, 610);
-    tc_fence_after();
-    if (elect_one_sync()) {
-      issue_ss(tS, sQ, sT);                                    // S(0)  = Q_i K_0^T
-      issue_ss(tmem_base + dp_col(0), sdO, sT + kTileBytes);   // dP(0) = dO_i V_0^T
+    // S(n) = Q_i K_n^T, dP(n) = dO_i V_n^T; the V slot is released by dP's own completion
+    auto issue_scores = [&](int n) {
+      const uint32_t sV = sT + slot_of(2 * n) * kTileBytes, sK = sT + slot_of(2 * n + 1) * kTileBytes;
+      issue_ss(tmem_base + dp_col(n), sdO, sV);
+      umma_commit(bar_t_empty + 8 * slot_of(2 * n));
+      issue_ss(tS, sQ, sK);
       umma_commit(bar_s_full);
-    }
+    };
+    mbar_wait(bar_f_full, 0, 600);
+    mbar_wait(bar_t_full + 8 * slot_of(0), phase_of(0), 610);
+    mbar_wait(bar_t_full + 8 * slot_of(1), phase_of(1), 611);
+    tc_fence_after();
+    if (elect_one_sync()) issue_scores(0);
     __syncwarp();
     for (int n = 0; n < steps; ++n) {
-      const int s = n & 1;
       if (n + 1 < steps) {
-        const int s1 = (n + 1) & 1;
-        const uint32_t sK1 = sT + (2 * s1) * kTileBytes;
-        mbar_wait(bar_t_full + 8 * s1, uint32_t((n + 1) >> 1) & 1u, 610 + s1);
+        mbar_wait(bar_t_full + 8 * slot_of(2 * n + 2), phase_of(2 * n + 2), 612);
+        mbar_wait(bar_t_full + 8 * slot_of(2 * n + 3), phase_of(2 * n + 3), 613);
         mbar_wait(bar_s_free, uint32_t(n) & 1u, 630);          // S(n) is in the compute warpgroups' registers
         tc_fence_after();
-        if (elect_one_sync()) {
-          issue_ss(tS, sQ, sK1);                                       // S(n+1)
-          issue_ss(tmem_base + dp_col(n + 1), sdO, sK1 + kTileBytes);  // dP(n+1) into the other dP buffer
-          umma_commit(bar_s_full);
-        }
+        if (elect_one_sync()) issue_scores(n + 1);             // dP(n+1) into the other dP buffer, S(n+1) over S(n)
         __syncwarp();
       }
       mbar_wait(bar_p_full, uint32_t(n) & 1u, 620);
       tc_fence_after();
       if (elect_one_sync()) {
         // dQ += dS(n) x K(n): k-steps 0..3 take keys 0..63 from dP columns 0..31, k-steps 4..7 keys 64..127 from 64..95
-        const uint32_t b_lo = lo_mn | ((sT + (2 * s) * kTileBytes) >> 4);
+        const uint32_t b_lo = lo_mn | ((sT + slot_of(2 * n + 1) * kTileBytes) >> 4);
         const uint32_t tdS = tmem_base + dp_col(n);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ts(tdQ, tdS + (k / 4) * kHalf + (k % 4) * 8, b_lo + k * (16 * kRowBytes / 16), hi_mn, a.idesc_ts,
                   (n > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bar_t_empty + 8 * s);
+        umma_commit(bar_t_empty + 8 * slot_of(2 * n + 1));
         if (n == steps - 1) umma_commit(bar_acc_full);
       }
       __syncwarp();

@@ -150,6 +150,12 @@ split_combine_kernel(const uint4* __restrict__ O_part, const float* __restrict__
   }
 }
 
+// 32-bit pattern fill (the ring driver's "lse = -inf" reset of its partial stack)
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* __restrict__ dst, uint32_t value, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = value;
+}
+
 // launched by fa_api.cu after the split-KV forward kernel
 int launch_split_combine(const void* O_part, const float* lse_part, const float* m_part, void* O, float* lse,
                          float* l, float* m, int nsplit, long long rows, int d, int H, int N, long long o_sb,
@@ -174,6 +180,13 @@ int launch_split_combine(const void* O_part, const float* lse_part, const float*
   else
     split_combine_kernel<false><<<grid_for(total), 256, 0, stream>>>((const uint4*)O_part, lse_part, m_part, (char*)O, lse, l,
                                                                      m, nsplit, rows, d, H, N, o_sb, o_sh, o_sn, st_sb, st_sh);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return FA_B200_OK;
+}
+int launch_fill_u32(uint32_t* dst, uint32_t value, long long count, cudaStream_t stream) {
+  fill_u32_kernel<<<grid_for(count), 256, 0, stream>>>(dst, value, count);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
   count_launch();

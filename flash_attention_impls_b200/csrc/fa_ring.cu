@@ -11,19 +11,30 @@
 //   * The pulls run through a window of TWO receive slots: the block of step s+1 lands while step s computes and the
 //     pull of step s+2 waits for step s's kernel, so the footprint is the ring's O(N/P): one published block + two
 //     receive slots, whatever P is.
-//   * Cross-rank ordering uses 32-bit sequence flags in the mapped memory instead of a collective: "my block of call
-//     n is published" (ready) and "I have pulled your block of call n" (ack) are 4-byte DMA writes into the peer's
-//     flag array, and the consumer waits with cuStreamWaitValue32 on its OWN memory - again no SM, no host sync, no
-//     NCCL kernel that would have to squeeze in between the persistent attention launches.
+//   * Cross-rank ordering uses interprocess CUDA EVENTS instead of a collective: "my block of call n is published"
+//     (ready) and "I have finished pulling in call n" (pulled) are events the owner records on its streams and the
+//     peers wait for with cudaStreamWaitEvent - no SM, no NCCL kernel that would have to squeeze in between the
+//     persistent attention launches, no device-side spinning.  An interprocess event wait only sees records that
+//     were ISSUED before it, so the ranks also keep one host-visible sequence counter each (a page of POSIX shared
+//     memory): a rank spins on the peer's counter (microseconds: all ranks enter the call together) until the peer
+//     has enqueued the record of this call, then enqueues its wait.  The device side stays fully asynchronous.
+//     (Stream memory operations - cuStreamWaitValue32 on flags in the mapped memory - would need no host counter, but
+//     on this pool's driver 580 the host call that enqueues work BEHIND a pending wait does not return until the value
+//     arrives, which deadlocks a rank that enqueues its own wait before its peer's write; the first version of this
+//     file hung that way.  Probe: tools/micro/memops_probe.cu, output in profiles/r02_memops_probe.log.)
 //   * The partial of every step goes into a slot of a preallocated stack and ONE HBM-bound pass merges them with
 //     their logsumexp at the end (fa_merge.cu).
 //
 // Causal runs use the zig-zag partition (rank r owns sequence chunks r and 2P-1-r), which turns every step into a
 // plain or square-causal call on (strided) row ranges with equal work on every rank - see the step loop.
-#include <cuda.h>
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -34,80 +45,82 @@
 namespace fa {
 int api_fail(int code, const char* msg);
 int api_check_device();
+int launch_fill_u32(uint32_t* dst, uint32_t value, long long count, cudaStream_t stream);   // fa_merge.cu
 }  // namespace fa
 
 namespace {
 
 constexpr int kMaxWorld = 64;
 constexpr uint64_t kMagic = 0x46413242474e4952ull;   // "FA2BGNIR"
-constexpr size_t kFlagBytes = 2 * kMaxWorld * sizeof(uint32_t);   // ready[64] | ack[64]
+
+// One page of shared host memory per rank: the call numbers whose event records this rank has already ISSUED.
+struct HostSync {
+  std::atomic<uint32_t> ready_seq;     // ev_ready[n & 1] of call n has been recorded (enqueued) on the owner's stream
+  std::atomic<uint32_t> pulled_seq;    // ev_pulled[n & 1] of call n has been recorded: every pull of call n is enqueued
+};
 
 struct RingExport {          // what fa_b200_ring_export writes: FA_B200_RING_EXPORT_BYTES
-  unsigned char ipc[64];     // cudaIpcMemHandle_t of the arena
   uint64_t magic;
-  uint64_t arena_ptr;        // the owner's address (used as is when the importer is the same process)
+  uint64_t arena_ptr;        // the owner's addresses, used as they are when the importer is the same process
+  uint64_t self_ptr;
   uint64_t block_bytes;
   int32_t pid, device, rank, world;
-  unsigned char pad[FA_B200_RING_EXPORT_BYTES - 64 - 3 * 8 - 4 * 4];
+  unsigned char ipc_mem[64];        // cudaIpcMemHandle_t of the arena
+  unsigned char ipc_event[4][64];   // cudaIpcEventHandle_t: ready[0], ready[1], pulled[0], pulled[1]
+  char shm_name[64];
+  unsigned char pad[FA_B200_RING_EXPORT_BYTES - 4 * 8 - 4 * 4 - 64 - 4 * 64 - 64];
 };
 static_assert(sizeof(RingExport) == FA_B200_RING_EXPORT_BYTES, "export blob size");
-
-using WaitValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-using MemsetD32AsyncFn = CUresult (*)(CUdeviceptr, unsigned int, size_t, CUstream);
-
-template <typename Fn>
-Fn driver_fn(const char* name) {
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-    return nullptr;
-  return reinterpret_cast<Fn>(p);
-}
+static_assert(sizeof(cudaIpcEventHandle_t) == 64 && sizeof(cudaIpcMemHandle_t) == 64, "IPC handle sizes");
 
 #define FA_TRY(call)                                                                      \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \
     if (e_ != cudaSuccess) return fa::api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e_)); \
   } while (0)
-#define FA_TRY_DRV(call, what)                                                                        \
-  do {                                                                                                \
-    CUresult r_ = (call);                                                                             \
-    if (r_ != CUDA_SUCCESS) {                                                                         \
-      char msg_[96];                                                                                  \
-      snprintf(msg_, sizeof(msg_), "%s failed with CUresult %d", what, (int)r_);                      \
-      return fa::api_fail(FA_B200_ERR_DRIVER, msg_);                                                  \
-    }                                                                                                 \
-  } while (0)
+
+// Host wait for a peer's sequence counter (the peer has entered the same call).  Bounded: a rank that never shows up
+// is reported instead of hanging the caller.
+bool spin_until(const std::atomic<uint32_t>* word, uint32_t seq, double timeout_s) {
+  if ((int32_t)(word->load(std::memory_order_acquire) - seq) >= 0) return true;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned it = 0;; ++it) {
+    if ((int32_t)(word->load(std::memory_order_acquire) - seq) >= 0) return true;
+    if ((it & 63) == 63) {
+      sched_yield();
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) return false;
+    }
+  }
+}
 
 }  // namespace
 
 struct fa_b200_ring {
   int world, rank, B, H, n_local, d, dtype, device;
   size_t blk;                       // bytes of one K (or V) block: B*H*n_local*d*2
-  char* arena;                      // K | V | flags, exported
-  size_t arena_bytes;
+  char* arena;                      // K | V, exported
   char* peer[kMaxWorld];            // mapped arenas (peer[rank] == arena)
-  bool peer_ipc[kMaxWorld];         // opened with cudaIpcOpenMemHandle (must be closed)
+  bool peer_ipc[kMaxWorld];         // opened through CUDA IPC (must be closed)
+  cudaEvent_t ev_ready[2], ev_pulled[2];              // mine, interprocess
+  cudaEvent_t peer_ready[kMaxWorld][2], peer_pulled[kMaxWorld][2];
+  HostSync* hs;                     // mine (shared memory)
+  const HostSync* peer_hs[kMaxWorld];
+  char shm_name[64];
   char* recv[2];                    // the two receive slots, K | V each
   char* o_parts;                    // [world][B,H,n_local,d] 16-bit partial outputs
   float* lse_parts;                 // [world][B,H,n_local]
-  uint32_t* seq_src;                // [2] device words holding the sequence number of call n (slot n & 1)
   cudaStream_t cs;                  // copy stream
-  cudaEvent_t ev_fork, ev_pull[2], ev_done[2];
+  cudaEvent_t ev_pull[2], ev_done[2];
   bool done_recorded[2];
   uint32_t seq;
-  uint32_t ack_waited;               // the call number whose "previous block consumed" waits are already enqueued
+  uint32_t consumed_waited;         // the call number whose "previous block consumed" waits are already enqueued
   bool connected;
-  WaitValue32Fn wait_value;
-  MemsetD32AsyncFn memset_d32;
+  double timeout_s;
   // optional timeline of the most recent call: per step begin / kv_ready / attn_done, then the combine
   bool profile;
   std::vector<cudaEvent_t> marks;
   int n_marks;
   size_t owned_bytes;
-
-  uint32_t* ready_flags(char* a) const { return reinterpret_cast<uint32_t*>(a + 2 * blk); }
-  uint32_t* ack_flags(char* a) const { return ready_flags(a) + kMaxWorld; }
 };
 
 extern "C" {
@@ -126,37 +139,49 @@ int fa_b200_ring_create(int world, int rank, int B, int H, int n_local, int d, i
   if (!r) return fa::api_fail(FA_B200_ERR_CUDA, "ring_create: out of host memory");
   r->world = world; r->rank = rank; r->B = B; r->H = H; r->n_local = n_local; r->d = d; r->dtype = dtype;
   r->blk = (size_t)B * H * n_local * d * 2;
-  r->arena_bytes = 2 * r->blk + kFlagBytes;
-  r->seq = 0; r->ack_waited = 0; r->connected = (world == 1); r->profile = false; r->n_marks = 0; r->owned_bytes = 0;
+  r->seq = 0; r->consumed_waited = 0; r->connected = (world == 1); r->profile = false; r->n_marks = 0; r->owned_bytes = 0;
+  r->timeout_s = 60.0;
+  if (const char* t = getenv("FA_B200_RING_TIMEOUT_S")) r->timeout_s = atof(t) > 0 ? atof(t) : r->timeout_s;
   cudaGetDevice(&r->device);
-  for (int i = 0; i < kMaxWorld; ++i) { r->peer[i] = nullptr; r->peer_ipc[i] = false; }
-  r->wait_value = driver_fn<WaitValue32Fn>("cuStreamWaitValue32");
-  r->memset_d32 = driver_fn<MemsetD32AsyncFn>("cuMemsetD32Async");
-  if (!r->wait_value || !r->memset_d32) {
-    delete r;
-    return fa::api_fail(FA_B200_ERR_DRIVER, "ring_create: cuStreamWaitValue32 / cuMemsetD32Async not available in this driver");
+  if (world == 1) {
+    *out = r;
+    return FA_B200_OK;
   }
+  // host-visible sequence counters in POSIX shared memory
+  static std::atomic<unsigned> counter{0};
+  snprintf(r->shm_name, sizeof(r->shm_name), "/fa_b200_ring_%d_%d_%u", (int)getpid(), rank, counter.fetch_add(1));
+  const char* err = nullptr;
+  int fd = shm_open(r->shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0 || ftruncate(fd, 4096) != 0) err = "ring_create: shm_open / ftruncate failed";
+  void* m = err ? MAP_FAILED : mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  if (fd >= 0) close(fd);
+  if (!err && m == MAP_FAILED) err = "ring_create: mmap of the shared counters failed";
+  if (err) {
+    r->shm_name[0] = 0;
+    fa_b200_ring_destroy(r);
+    return fa::api_fail(FA_B200_ERR_CUDA, err);
+  }
+  r->hs = new (m) HostSync();
+  r->hs->ready_seq.store(0);
+  r->hs->pulled_seq.store(0);
+  r->peer_hs[rank] = r->hs;
+
   cudaError_t e = cudaSuccess;
   const size_t stat = (size_t)B * H * n_local * sizeof(float);
-  if (world > 1) {
-    e = cudaMalloc((void**)&r->arena, r->arena_bytes);
-    if (e == cudaSuccess) e = cudaMemset(r->arena + 2 * r->blk, 0, kFlagBytes);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc((void**)&r->recv[i], 2 * r->blk);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->o_parts, (size_t)world * r->blk);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->lse_parts, (size_t)world * stat);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->seq_src, 2 * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(r->seq_src, 0, 2 * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->cs, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-      e = cudaEventCreateWithFlags(&r->ev_pull[i], cudaEventDisableTiming);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_done[i], cudaEventDisableTiming);
-      r->done_recorded[i] = false;
-    }
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the zeroed flags are in place before anyone can connect
-    r->owned_bytes = r->arena_bytes + 4 * r->blk + (size_t)world * (r->blk + stat) + 8;
-    r->peer[rank] = r->arena;
+  e = cudaMalloc((void**)&r->arena, 2 * r->blk);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc((void**)&r->recv[i], 2 * r->blk);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&r->o_parts, (size_t)world * r->blk);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&r->lse_parts, (size_t)world * stat);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->cs, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&r->ev_pull[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_ready[i], cudaEventDisableTiming | cudaEventInterprocess);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_pulled[i], cudaEventDisableTiming | cudaEventInterprocess);
+    r->done_recorded[i] = false;
   }
+  r->owned_bytes = 6 * r->blk + (size_t)world * (r->blk + stat);
+  r->peer[rank] = r->arena;
   if (e != cudaSuccess) {
     fa_b200_ring_destroy(r);
     return fa::api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
@@ -171,13 +196,21 @@ int fa_b200_ring_export(const fa_b200_ring* r, unsigned char blob[FA_B200_RING_E
   memset(&x, 0, sizeof(x));
   x.magic = kMagic;
   x.arena_ptr = reinterpret_cast<uint64_t>(r->arena);
+  x.self_ptr = reinterpret_cast<uint64_t>(r);
   x.block_bytes = r->blk;
   x.pid = (int32_t)getpid();
   x.device = r->device; x.rank = r->rank; x.world = r->world;
   if (r->world > 1) {
     cudaIpcMemHandle_t h;
     FA_TRY(cudaIpcGetMemHandle(&h, r->arena));
-    memcpy(x.ipc, &h, 64);
+    memcpy(x.ipc_mem, &h, 64);
+    const cudaEvent_t evs[4] = {r->ev_ready[0], r->ev_ready[1], r->ev_pulled[0], r->ev_pulled[1]};
+    for (int i = 0; i < 4; ++i) {
+      cudaIpcEventHandle_t eh;
+      FA_TRY(cudaIpcGetEventHandle(&eh, evs[i]));
+      memcpy(x.ipc_event[i], &eh, 64);
+    }
+    memcpy(x.shm_name, r->shm_name, sizeof(x.shm_name));
   }
   memcpy(blob, &x, sizeof(x));
   return FA_B200_OK;
@@ -197,19 +230,33 @@ int fa_b200_ring_connect(fa_b200_ring* r, const unsigned char* blobs) {
     if (p == r->rank) continue;
     if (x.pid == (int32_t)getpid()) {
       // several ranks in one process (one host thread per GPU, or the single-GPU protocol test): no IPC needed
+      const fa_b200_ring* o = reinterpret_cast<const fa_b200_ring*>(x.self_ptr);
       if (x.device != r->device) {
         cudaError_t e = cudaDeviceEnablePeerAccess(x.device, 0);
         if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
         else if (e != cudaSuccess) return fa::api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
       }
-      r->peer[p] = reinterpret_cast<char*>(x.arena_ptr);
+      r->peer[p] = o->arena;
+      for (int i = 0; i < 2; ++i) { r->peer_ready[p][i] = o->ev_ready[i]; r->peer_pulled[p][i] = o->ev_pulled[i]; }
+      r->peer_hs[p] = o->hs;
     } else {
       cudaIpcMemHandle_t h;
-      memcpy(&h, x.ipc, 64);
+      memcpy(&h, x.ipc_mem, 64);
       void* ptr = nullptr;
       FA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
       r->peer[p] = static_cast<char*>(ptr);
       r->peer_ipc[p] = true;
+      for (int i = 0; i < 4; ++i) {
+        cudaIpcEventHandle_t eh;
+        memcpy(&eh, x.ipc_event[i], 64);
+        FA_TRY(cudaIpcOpenEventHandle(i < 2 ? &r->peer_ready[p][i] : &r->peer_pulled[p][i - 2], eh));
+      }
+      x.shm_name[sizeof(x.shm_name) - 1] = 0;
+      int fd = shm_open(x.shm_name, O_RDONLY, 0);
+      void* m = fd < 0 ? MAP_FAILED : mmap(nullptr, 4096, PROT_READ, MAP_SHARED, fd, 0);
+      if (fd >= 0) close(fd);
+      if (m == MAP_FAILED) return fa::api_fail(FA_B200_ERR_CUDA, "ring_connect: cannot map a peer's shared counters (ranks on different hosts?)");
+      r->peer_hs[p] = static_cast<const HostSync*>(m);
     }
   }
   r->connected = true;
@@ -223,17 +270,20 @@ int fa_b200_ring_kv_buffers(fa_b200_ring* r, void** k_buf, void** v_buf) {
   return FA_B200_OK;
 }
 
-// Enqueues on `stream` the wait for "every peer has pulled the block I published in the previous call".  forward()
-// does this itself before it overwrites the publish buffers; a caller that writes K/V straight into those buffers
+// Orders `st` behind "every peer has pulled the block I published in the previous call".  forward() does this itself
+// before it overwrites the publish buffers; a caller that writes K/V straight into those buffers
 // (fa_b200_ring_kv_buffers) calls it before the kernel that produces the next K/V.
 static int wait_consumed(fa_b200_ring* r, cudaStream_t st) {
-  const uint32_t next = r->seq + 1;
-  if (r->world == 1 || r->ack_waited == next) return FA_B200_OK;
-  for (int p = 0; p < r->world; ++p)
-    if (p != r->rank)
-      FA_TRY_DRV(r->wait_value(st, reinterpret_cast<CUdeviceptr>(r->ack_flags(r->arena) + p), next - 1, CU_STREAM_WAIT_VALUE_GEQ),
-                 "cuStreamWaitValue32(ack)");
-  r->ack_waited = next;
+  const uint32_t next = r->seq + 1, prev = r->seq;
+  if (r->world == 1 || r->consumed_waited == next) return FA_B200_OK;
+  if (prev > 0)
+    for (int p = 0; p < r->world; ++p) {
+      if (p == r->rank) continue;
+      if (!spin_until(&r->peer_hs[p]->pulled_seq, prev, r->timeout_s))
+        return fa::api_fail(FA_B200_ERR_CUDA, "ring: a peer did not finish enqueuing the previous ring forward (timeout)");
+      FA_TRY(cudaStreamWaitEvent(st, r->peer_pulled[p][prev & 1u], 0));
+    }
+  r->consumed_waited = next;
   return FA_B200_OK;
 }
 
@@ -314,33 +364,34 @@ int fa_b200_ring_forward(fa_b200_ring* r, const void* Q, const void* K, const vo
   }
 
   FA_TRY(note());   // mark 0: call start
-  // 1. my published block of the previous call has been pulled by everyone (acks arrive long before this point)
+  // 1. the block I published in the previous call has been pulled by everyone (true long before this point)
   int rc = wait_consumed(r, st);
   if (rc) return rc;
   const uint32_t seq = ++r->seq;
-  uint32_t* seq_word = r->seq_src + (seq & 1u);
-  // 2. publish (skipped when the caller already keeps K/V in the ring's own buffers, fa_b200_ring_kv_buffers)
+  const int par = int(seq & 1u);
+  // 2. publish (skipped when the caller already keeps K/V in the ring's own buffers, fa_b200_ring_kv_buffers),
+  //    record "ready", and tell the peers' hosts that the record of this call has been issued
   if (K != r->arena) FA_TRY(cudaMemcpyAsync(r->arena, K, r->blk, cudaMemcpyDeviceToDevice, st));
   if (V != r->arena + r->blk) FA_TRY(cudaMemcpyAsync(r->arena + r->blk, V, r->blk, cudaMemcpyDeviceToDevice, st));
-  // 3. tell every peer: 4-byte DMA write of the sequence number into its ready[me]
-  FA_TRY_DRV(r->memset_d32(reinterpret_cast<CUdeviceptr>(seq_word), seq, 1, st), "cuMemsetD32Async");
-  for (int p = 0; p < P; ++p)
-    if (p != me)
-      FA_TRY(cudaMemcpyAsync(r->ready_flags(r->peer[p]) + me, seq_word, sizeof(uint32_t), cudaMemcpyDefault, st));
-  FA_TRY(cudaEventRecord(r->ev_fork, st));
-  FA_TRY(cudaStreamWaitEvent(r->cs, r->ev_fork, 0));
+  FA_TRY(cudaEventRecord(r->ev_ready[par], st));
+  r->hs->ready_seq.store(seq, std::memory_order_release);
   // every slot row a step does not compute keeps lse = -inf and is skipped by the combine
-  FA_TRY_DRV(r->memset_d32(reinterpret_cast<CUdeviceptr>(r->lse_parts), 0xff800000u, (size_t)P * stat, st), "cuMemsetD32Async");
+  if ((rc = fa::launch_fill_u32(reinterpret_cast<uint32_t*>(r->lse_parts), 0xff800000u, (long long)P * stat, st))) return rc;
 
-  // Pull of step s into receive slot s & 1 (enqueued on the copy stream).
+  // Pull of step s into receive slot s & 1 (enqueued on the copy stream): wait for the slot's last reader and for the
+  // owner's "ready" of THIS call, copy K|V in one piece, record.
   auto enqueue_pull = [&](int s) -> int {
     const int src = (me - s + P) % P, slot = s & 1;
-    if (r->done_recorded[slot]) FA_TRY(cudaStreamWaitEvent(r->cs, r->ev_done[slot], 0));   // last reader of the slot
-    FA_TRY_DRV(r->wait_value(r->cs, reinterpret_cast<CUdeviceptr>(r->ready_flags(r->arena) + src), seq, CU_STREAM_WAIT_VALUE_GEQ),
-               "cuStreamWaitValue32(ready)");
+    if (!spin_until(&r->peer_hs[src]->ready_seq, seq, r->timeout_s))
+      return fa::api_fail(FA_B200_ERR_CUDA, "ring_forward: a peer did not enter this ring forward (timeout); every rank must call it");
+    if (r->done_recorded[slot]) FA_TRY(cudaStreamWaitEvent(r->cs, r->ev_done[slot], 0));
+    FA_TRY(cudaStreamWaitEvent(r->cs, r->peer_ready[src][par], 0));
     FA_TRY(cudaMemcpyAsync(r->recv[slot], r->peer[src], 2 * r->blk, cudaMemcpyDefault, r->cs));
     FA_TRY(cudaEventRecord(r->ev_pull[slot], r->cs));
-    FA_TRY(cudaMemcpyAsync(r->ack_flags(r->peer[src]) + me, seq_word, sizeof(uint32_t), cudaMemcpyDefault, r->cs));
+    if (s == P - 1) {   // the last pull of the call: "I am done pulling"
+      FA_TRY(cudaEventRecord(r->ev_pulled[par], r->cs));
+      r->hs->pulled_seq.store(seq, std::memory_order_release);
+    }
     return FA_B200_OK;
   };
 
@@ -367,10 +418,8 @@ int fa_b200_ring_forward(fa_b200_ring* r, const void* Q, const void* K, const vo
       r->done_recorded[slot] = true;
     }
     FA_TRY(note());
-    if (s + 2 < P) {
-      // slot (s+2)&1 == slot of step s (for s >= 1) or the slot nobody used yet in this call (s == 0)
-      if ((rc = enqueue_pull(s + 2))) return rc;
-    }
+    // window of two slots: the pull of step s+2 reuses the slot of step s (s >= 1) or the still unused one (s == 0)
+    if (s + 2 < P && (rc = enqueue_pull(s + 2))) return rc;
   }
   rc = fa_b200_combine_partials(r->o_parts, r->lse_parts, P, O, lse, (int64_t)stat, d, r->dtype, st);
   if (rc) return rc;
@@ -385,20 +434,29 @@ int fa_b200_ring_destroy(fa_b200_ring* r) {
   cudaGetDevice(&prev);
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
-  for (int p = 0; p < kMaxWorld; ++p)
-    if (r->peer_ipc[p] && r->peer[p]) cudaIpcCloseMemHandle(r->peer[p]);
+  for (int p = 0; p < kMaxWorld; ++p) {
+    if (!r->peer_ipc[p]) continue;
+    if (r->peer[p]) cudaIpcCloseMemHandle(r->peer[p]);
+    for (int i = 0; i < 2; ++i) {
+      if (r->peer_ready[p][i]) cudaEventDestroy(r->peer_ready[p][i]);
+      if (r->peer_pulled[p][i]) cudaEventDestroy(r->peer_pulled[p][i]);
+    }
+    if (r->peer_hs[p]) munmap(const_cast<HostSync*>(r->peer_hs[p]), 4096);
+  }
   if (r->arena) cudaFree(r->arena);
   for (int i = 0; i < 2; ++i) {
     if (r->recv[i]) cudaFree(r->recv[i]);
     if (r->ev_pull[i]) cudaEventDestroy(r->ev_pull[i]);
     if (r->ev_done[i]) cudaEventDestroy(r->ev_done[i]);
+    if (r->ev_ready[i]) cudaEventDestroy(r->ev_ready[i]);
+    if (r->ev_pulled[i]) cudaEventDestroy(r->ev_pulled[i]);
   }
   if (r->o_parts) cudaFree(r->o_parts);
   if (r->lse_parts) cudaFree(r->lse_parts);
-  if (r->seq_src) cudaFree(r->seq_src);
   if (r->cs) cudaStreamDestroy(r->cs);
-  if (r->ev_fork) cudaEventDestroy(r->ev_fork);
   for (cudaEvent_t ev : r->marks) cudaEventDestroy(ev);
+  if (r->hs) munmap(r->hs, 4096);
+  if (r->shm_name[0]) shm_unlink(r->shm_name);
   cudaGetLastError();
   cudaSetDevice(prev);
   delete r;

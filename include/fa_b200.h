@@ -198,18 +198,19 @@ int fa_b200_copy_async(void* dst, const void* src, size_t bytes, void* stream);
  * One handle per GPU (one process or host thread per GPU), single node.  The sequence is split over `world` ranks;
  * rank r holds Q, K, V rows [B,H,n_local,d] (dense).  A forward runs `world` steps; step s attends the local queries
  * to the K/V block of rank (r - s) mod world, which is PULLED from its owner's exported buffer by the copy engines
- * (no SM, no NCCL kernel) through a window of two receive slots, ordered by 32-bit sequence flags in the mapped
- * memory (4-byte DMA writes + cuStreamWaitValue32; no collective, no host synchronisation).  The partials are merged
- * with their logsumexp.  Causal rings use the zig-zag partition: the local rows of rank r are sequence chunks r and
+ * (no SM, no NCCL kernel) through a window of two receive slots, ordered by interprocess CUDA events (no collective,
+ * no device-side spinning; the ranks' hosts exchange one sequence counter each through a page of POSIX shared memory,
+ * so a forward may hold the calling host thread for the few microseconds until every peer has ENTERED the same
+ * call - one host thread per rank).  The partials are merged with their logsumexp.  Causal rings use the zig-zag partition: the local rows of rank r are sequence chunks r and
  * 2*world-1-r (of 2*world equal chunks), in that order; non-causal rings accept any equal partition.
  *
  * Life cycle:  create (allocates everything the handle will ever use: one published K|V block, two receive slots,
- * the partial stack - fa_b200_ring_device_bytes reports it; forward never allocates)  ->  export (a 128-byte blob)
+ * the partial stack - fa_b200_ring_device_bytes reports it; forward never allocates)  ->  export (a 512-byte blob)
  * -> the CALLER exchanges the blobs between ranks by any means (MPI, torch.distributed, a file)  ->  connect (maps
  * the peers; blobs in rank order)  ->  forward, any number of times, collectively (every rank the same number of
  * calls)  ->  destroy (collective: no rank may still be pulling; synchronise the ranks first).
  * Ranks living in the same process (one host thread per GPU) connect without IPC. */
-#define FA_B200_RING_EXPORT_BYTES 128
+#define FA_B200_RING_EXPORT_BYTES 512
 typedef struct fa_b200_ring fa_b200_ring;
 int fa_b200_ring_create(int world, int rank, int B, int H, int n_local, int d, int dtype, fa_b200_ring** out);
 int fa_b200_ring_export(const fa_b200_ring* ring, unsigned char blob[FA_B200_RING_EXPORT_BYTES]);

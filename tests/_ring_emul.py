@@ -1,19 +1,21 @@
 """Single-process, single-GPU run of the C-ABI ring (`fa_b200_ring_*`) with world_size > 1.
 
 Ranks that live in the same process connect without CUDA IPC (csrc/fa_ring.cu), so the complete protocol -
-publish, ready/ack sequence flags, copy-engine pulls through the two-slot window, zig-zag step schedule,
-one-pass combine - runs with real world_size-2/4 semantics on the ONE GPU of the driver's test box.  Every rank
-gets its own stream; a forward is enqueue-only, so the host enqueues rank 0's whole call (which waits, on the
-device, for flags that rank 1 has not even enqueued yet) and then the others.
+publish, ready / pulled events with their host sequence counters, copy-engine pulls through the two-slot window,
+zig-zag step schedule, one-pass combine - runs with real world_size-2/3/4 semantics on the ONE GPU of the driver's
+test box.  Every rank gets its own host thread and its own stream, as the C ABI prescribes (a forward holds its host
+thread until every peer has entered the same call; ctypes releases the GIL during the call).
 
-Run by tests/test_ring_gpu.py in a subprocess under a timeout (a protocol bug would leave streams waiting on a
-flag forever; the subprocess dies and takes its waits with it).  Prints one line starting with PASS or FAIL.
+Run by tests/test_ring_gpu.py in a subprocess under a timeout, and every wait in here is bounded, so a protocol bug
+is reported instead of hanging the session.  Prints one line starting with PASS or FAIL.
 """
 import ctypes
 import os
 import sys
+import threading
+import time
 
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream: no false dependencies
+os.environ.setdefault("FA_B200_RING_TIMEOUT_S", "20")        # a rank that never shows up is an error after 20 s, not a hang
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
@@ -60,27 +62,31 @@ def main():
         outs = [torch.empty((B, H, Nl, d), dtype=torch.bfloat16, device=dev) for _ in range(world)]
         lses = [torch.empty((B, H, Nl), dtype=torch.float32, device=dev) for _ in range(world)]
         torch.cuda.synchronize()
-        for r in range(world):
+        status = [None] * world
+
+        def run_rank(r):
             ql, kl, vl = shards[r]
-            _lib.check(lib.fa_b200_ring_forward(rings[r], ql.data_ptr(), kl.data_ptr(), vl.data_ptr(), outs[r].data_ptr(),
-                                                lses[r].data_ptr(), 1 if causal else 0, 0.0, streams[r].cuda_stream))
-        # never block on a device-side wait that might not be satisfied: poll the streams with a deadline and, if they
-        # do not drain, dump the sequence flags (which rank is waiting for whom) before giving up
-        import time
+            torch.cuda.set_device(dev)
+            status[r] = lib.fa_b200_ring_forward(rings[r], ql.data_ptr(), kl.data_ptr(), vl.data_ptr(), outs[r].data_ptr(),
+                                                 lses[r].data_ptr(), 1 if causal else 0, 0.0, streams[r].cuda_stream)
+            if status[r]:
+                status[r] = (status[r], lib.fa_b200_last_error().decode())
+
+        threads = [threading.Thread(target=run_rank, args=(r,), daemon=True) for r in range(world)]
+        for t_ in threads:
+            t_.start()
+        for t_ in threads:
+            t_.join(timeout=40.0)
+        if any(t_.is_alive() for t_ in threads) or any(status):
+            print(f"FAIL world={world} causal={int(causal)} call={call}: host side, alive={[t_.is_alive() for t_ in threads]} "
+                  f"status={status}", flush=True)
+            os._exit(1)
         deadline = time.time() + 30.0
         while not all(s_.query() for s_ in streams) and time.time() < deadline:
             time.sleep(0.01)
         if not all(s_.query() for s_ in streams):
-            side = torch.cuda.Stream(dev)
-            dump = torch.zeros(128, dtype=torch.int32, device=dev)
-            for r in range(world):
-                kb, vb = ctypes.c_void_p(), ctypes.c_void_p()
-                lib.fa_b200_ring_kv_buffers(rings[r], ctypes.byref(kb), ctypes.byref(vb))
-                lib.fa_b200_copy_async(dump.data_ptr(), kb.value + 2 * block, 512, side.cuda_stream)
-                side.synchronize()
-                fl = dump.cpu().tolist()
-                print(f"STUCK call={call} rank={r} stream_done={streams[r].query()} ready={fl[:world]} ack={fl[64:64 + world]}", flush=True)
-            print(f"FAIL world={world} causal={int(causal)}: streams did not drain within 30 s", flush=True)
+            print(f"FAIL world={world} causal={int(causal)} call={call}: streams did not drain within 30 s: "
+                  f"{[s_.query() for s_ in streams]}", flush=True)
             os._exit(1)
         torch.cuda.synchronize()
         if causal:
@@ -96,8 +102,8 @@ def main():
     for h in rings:
         lib.fa_b200_ring_destroy(h)
     ok = worst_o <= 2e-3 and worst_l <= 1e-4 and worst_single <= 4e-3
-    # footprint: published block (K|V) + two receive slots (K|V each) + the partial stack (world outputs + lse) + flags
-    want = 3 * 2 * block + world * (block + B * H * Nl * 4) + 2 * 64 * 4 + 8
+    # footprint: published block (K|V) + two receive slots (K|V each) + the partial stack (world outputs + lse)
+    want = 3 * 2 * block + world * (block + B * H * Nl * 4)
     ok = ok and owned == want
     print(f"{'PASS' if ok else 'FAIL'} world={world} causal={int(causal)} calls={calls} o_err={worst_o:.3e} "
           f"lse_rel={worst_l:.3e} vs_single_gpu={worst_single:.3e} handle_bytes={owned} (= {owned / (2 * block):.2f} K|V blocks)")

@@ -71,10 +71,10 @@ def test_ring_attention_nccl(causal, transport):
 # ------------------------------------------------------------------------------ the C-ABI ring (fa_b200_ring_*)
 @pytest.mark.parametrize("world,causal", [(2, True), (2, False), (4, True), (3, True)])
 def test_c_abi_ring_protocol_on_one_gpu(world, causal):
-    """world_size 2/3/4 of the C-ABI ring on ONE GPU (ranks in one process connect without IPC): ready/ack flags,
-    two-slot pull window, zig-zag schedule and combine, three back-to-back calls, against the oracle and against a
-    single attention_forward over the whole sequence.  Runs in a subprocess under a timeout so that a protocol bug
-    (a stream waiting on a flag forever) cannot hang the test session."""
+    """world_size 2/3/4 of the C-ABI ring on ONE GPU (ranks in one process, one host thread each, connect without IPC):
+    ready / pulled events and their host counters, two-slot pull window, zig-zag schedule and combine, three
+    back-to-back calls, against the oracle and against a single attention_forward over the whole sequence.  Runs in a
+    subprocess under a timeout, with every wait inside bounded, so a protocol bug cannot hang the test session."""
     import subprocess
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ring_emul.py"), str(world), str(int(causal)), "3"],
                        capture_output=True, text=True, timeout=120)

@@ -33,6 +33,7 @@ static bool wait_done(cudaStream_t a, cudaStream_t b, double seconds) {
 }
 
 int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);   // a hung case must not swallow the lines before it
   CK(cudaSetDevice(0));
   CK(cudaFree(0));
   int v = 0;
@@ -61,7 +62,11 @@ int main() {
     const uint32_t seq = 7;
     unsigned int wflags = CU_STREAM_WAIT_VALUE_GEQ | (mode == 4 ? CU_STREAM_WAIT_VALUE_FLUSH : 0);
     // waiter first (as the ring does: rank 0's whole call is enqueued before rank 1's)
+    printf("case %d: enqueuing the wait ...\n", mode);
+    const auto c0 = std::chrono::steady_clock::now();
     CKD(cuStreamWaitValue32((CUstream)A, (CUdeviceptr)flag, seq, wflags));
+    printf("  cuStreamWaitValue32 returned after %.3f ms\n",
+           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count());
     if (mode == 3) spin_kernel<<<1, 32, 0, A>>>(1000);
     CK(cudaMemcpyAsync(big, big + (8 << 20), 32 << 20, cudaMemcpyDeviceToDevice, A));
     // some work on B before the raise
