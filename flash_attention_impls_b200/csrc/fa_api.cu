@@ -70,6 +70,10 @@ EncodeTiledFn get_encode_fn() {
 // swizzle).  Out-of-range rows read as zero and are clipped on store, which is what makes ragged N work.
 int encode_tmap(CUtensorMap* tm, unsigned* perm, const void* base, int dtype, int d, long long rows, long long H,
               long long B, long long sn, long long sh, long long sb) {
+  // `d` is the tensor's real head_dim; the kernel instantiation (and with it the box) is the next of 32 / 64 / 128.
+  // Columns of a box beyond d are out of bounds: TMA reads them as zeros and clips them on store, which is all a
+  // head_dim between the instantiated sizes needs (zero columns add nothing to q.k and produce zero output columns).
+  const int dk = d <= 32 ? 32 : (d <= 64 ? 64 : 128);
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   struct Axis { long long size, stride; unsigned role; cuuint32_t box; };
@@ -80,7 +84,7 @@ int encode_tmap(CUtensorMap* tm, unsigned* perm, const void* base, int dtype, in
     for (int j = i; j > 0 && key(ax[j]) < key(ax[j - 1]); --j) std::swap(ax[j], ax[j - 1]);
   cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)ax[0].size, (cuuint64_t)ax[1].size, (cuuint64_t)ax[2].size};
   cuuint64_t strides[3];
-  cuuint32_t box[4] = {(cuuint32_t)(d >= 64 ? 64 : 32), ax[0].box, ax[1].box, ax[2].box};
+  cuuint32_t box[4] = {(cuuint32_t)(dk >= 64 ? 64 : 32), ax[0].box, ax[1].box, ax[2].box};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   unsigned long long prev_extent = (unsigned long long)d * 2;
   *perm = 0;
@@ -93,7 +97,7 @@ int encode_tmap(CUtensorMap* tm, unsigned* perm, const void* base, int dtype, in
   }
   CUresult r = enc(tm, dtype == FA_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                    4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   d >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   dk >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FA_B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return FA_B200_OK;
@@ -359,7 +363,7 @@ extern "C" {
 
 int fa_b200_work_item(int B, int H, int N, int N_kv, int d, int causal, int index, int* bh, int* q0,
                       int* tiles0, int* tiles1) {
-  if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || (d != 32 && d != 64 && d != 128)) {
+  if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || d < 8 || d > 128 || (d % 8)) {
     fail(FA_B200_ERR_SHAPE, "work_item: bad shape");
     return 0;
   }
@@ -378,7 +382,7 @@ int fa_b200_work_item(int B, int H, int N, int N_kv, int d, int causal, int inde
 }
 
 size_t fa_b200_workspace_bytes(int B, int H, int N, int N_kv, int d) {
-  if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || (d != 32 && d != 64 && d != 128)) return 0;
+  if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || d < 8 || d > 128 || (d % 8)) return 0;
   const int Nkv = N_kv ? N_kv : N;
   const long long items = (long long)B * H * ((N + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM));
   const int nsplit = choose_nsplit(items, (Nkv + fa::kBlockN - 1) / fa::kBlockN, sm_count());
@@ -390,13 +394,17 @@ int fa_b200_forward(const fa_b200_params* p) {
   if (!p->Q || !p->K || !p->V || !p->O) return fail(FA_B200_ERR_NULL, "Q, K, V and O must be non-NULL");
   if (p->B <= 0 || p->H <= 0 || p->N <= 0 || p->N_kv < 0)
     return fail(FA_B200_ERR_SHAPE, "bad shape B=%d H=%d N=%d N_kv=%d", p->B, p->H, p->N, p->N_kv);
-  if (p->d != 32 && p->d != 64 && p->d != 128)
-    return fail(FA_B200_ERR_HEAD_DIM, "unsupported head_dim=%d (supported: 32, 64, 128)", p->d);
+  if (p->d < 8 || p->d > 128 || (p->d % 8))
+    return fail(FA_B200_ERR_HEAD_DIM, "unsupported head_dim=%d (supported: multiples of 8 up to 128)", p->d);
   if (p->dtype != FA_B200_FP16 && p->dtype != FA_B200_BF16)
     return fail(FA_B200_ERR_DTYPE, "unsupported dtype=%d (0 = fp16, 1 = bf16)", p->dtype);
   const long long BH = (long long)p->B * p->H;
   const int Nq = p->N, Nkv = p->N_kv ? p->N_kv : p->N;
   const int d = p->d;
+  // kernel instantiation: the next of 32 / 64 / 128 (the reference's dispatch set, flash_attn_cutlass.cu:530-542); a
+  // head_dim in between runs it with the surplus columns read as zeros by TMA and clipped on store (see encode_tmap) -
+  // the reference's FA1 kernel takes any d <= 128 (flashAttention.cu:86) and its Triton path D % 16 == 0 (FA2-triton.py:177)
+  const int dk = d <= 32 ? 32 : (d <= 64 ? 64 : 128);
   const long long num_q_blocks = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
   if (BH * num_q_blocks > 0x7fffffffLL) return fail(FA_B200_ERR_SHAPE, "B*H*ceil(N/256) exceeds the grid limit");
   // strides: 0 => dense [B,H,N,d] default
@@ -463,7 +471,7 @@ int fa_b200_forward(const fa_b200_params* p) {
   a.perm_kv = perm_kv;
   a.perm_o = perm_o;
   const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;
-  if (d >= 64) {
+  if (dk >= 64) {
     // Q, K: K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.
     a.desc_hi_qk = fa::umma_desc_hi_bits(16, 1024, 2);
     // V: MN-major (d contiguous), 128B swizzle: 64-column halves one box (16 KB) apart (LBO),
@@ -475,7 +483,7 @@ int fa_b200_forward(const fa_b200_params* p) {
     a.desc_hi_v = fa::umma_desc_hi_bits(fa::FwdTraits<32>::kBoxBytes, 512, 4);
   }
   a.idesc_qk = fa::umma_idesc(fmt, 0, 0, 128, 128);
-  a.idesc_pv = fa::umma_idesc(fmt, 0, 1, 128, (unsigned)d);
+  a.idesc_pv = fa::umma_idesc(fmt, 0, 1, 128, (unsigned)dk);
 #ifdef FA_B200_DEBUG   // bring-up overrides
   a.desc_hi_qk = env_u64("FA_B200_DESC_HI_QK", a.desc_hi_qk);
   a.desc_hi_v = env_u64("FA_B200_DESC_HI_V", a.desc_hi_v);
@@ -501,10 +509,10 @@ int fa_b200_forward(const fa_b200_params* p) {
 #define FA_LAUNCH(D_, BF_, C_)                                                             \
   rc = precise ? launch<D_, BF_, C_, true>(tq, tk, tv, to, a, grid, stream)                \
                : launch<D_, BF_, C_, false>(tq, tk, tv, to, a, grid, stream)
-  if (d == 128) {
+  if (dk == 128) {
     if (bf16) { if (causal) FA_LAUNCH(128, true, true); else FA_LAUNCH(128, true, false); }
     else      { if (causal) FA_LAUNCH(128, false, true); else FA_LAUNCH(128, false, false); }
-  } else if (d == 32) {
+  } else if (dk == 32) {
     if (bf16) { if (causal) FA_LAUNCH(32, true, true); else FA_LAUNCH(32, true, false); }
     else      { if (causal) FA_LAUNCH(32, false, true); else FA_LAUNCH(32, false, false); }
   } else {

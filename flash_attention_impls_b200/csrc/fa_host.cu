@@ -43,7 +43,7 @@ extern "C" int fa_b200_host_ctx_create(int B, int H, int N, int d, int dtype, in
   if (!out) return fa::api_fail(FA_B200_ERR_NULL, "host_ctx_create: out is NULL");
   *out = nullptr;
   if (B <= 0 || H <= 0 || N <= 0) return fa::api_fail(FA_B200_ERR_SHAPE, "host_ctx_create: bad shape");
-  if (d != 32 && d != 64 && d != 128) return fa::api_fail(FA_B200_ERR_HEAD_DIM, "host_ctx_create: unsupported head_dim");
+  if (d < 8 || d > 128 || (d % 8)) return fa::api_fail(FA_B200_ERR_HEAD_DIM, "host_ctx_create: unsupported head_dim (multiples of 8 up to 128)");
   if (dtype != FA_B200_FP16 && dtype != FA_B200_BF16) return fa::api_fail(FA_B200_ERR_DTYPE, "host_ctx_create: bad dtype");
   int rc = fa::api_check_device();
   if (rc) return rc;

@@ -24,7 +24,7 @@ void run(const char* who, const void* Q, const void* K, const void* V, void* O, 
          cudaStream_t stream) {
   int rc = fa_b200_forward_fp16(Q, K, V, O, B, H, N, d, stream);
   if (rc == FA_B200_ERR_HEAD_DIM)
-    fprintf(stderr, "Unsupported head_dim=%d for %s (supported: 32, 64, 128)\n", d, who);
+    fprintf(stderr, "Unsupported head_dim=%d for %s (supported: multiples of 8 up to 128)\n", d, who);
   else if (rc != FA_B200_OK)
     fprintf(stderr, "%s failed: %s (%s)\n", who, fa_b200_status_string(rc), fa_b200_last_error());
 }

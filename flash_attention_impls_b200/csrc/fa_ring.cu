@@ -131,7 +131,7 @@ int fa_b200_ring_create(int world, int rank, int B, int H, int n_local, int d, i
   if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
     return fa::api_fail(FA_B200_ERR_SHAPE, "ring_create: need 1 <= world <= 64 and 0 <= rank < world");
   if (B <= 0 || H <= 0 || n_local <= 0) return fa::api_fail(FA_B200_ERR_SHAPE, "ring_create: B, H, n_local must be positive");
-  if (d != 32 && d != 64 && d != 128) return fa::api_fail(FA_B200_ERR_HEAD_DIM, "ring_create: unsupported head_dim (32, 64, 128)");
+  if (d < 8 || d > 128 || (d % 8)) return fa::api_fail(FA_B200_ERR_HEAD_DIM, "ring_create: unsupported head_dim (multiples of 8 up to 128)");
   if (dtype != FA_B200_FP16 && dtype != FA_B200_BF16) return fa::api_fail(FA_B200_ERR_DTYPE, "ring_create: bad dtype");
   int rc = fa::api_check_device();
   if (rc) return rc;

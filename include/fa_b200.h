@@ -42,7 +42,8 @@ enum fa_b200_status {
   FA_B200_OK = 0,
   FA_B200_ERR_NULL = 1,        /* a required pointer is NULL */
   FA_B200_ERR_SHAPE = 2,       /* B,H,N <= 0, N_kv < 0, B*H too large */
-  FA_B200_ERR_HEAD_DIM = 3,    /* d not in {32,64,128} (the set the reference dispatches on, flash_attn_cutlass.cu:530-542) */
+  FA_B200_ERR_HEAD_DIM = 3,    /* forward: d not a multiple of 8 in [8,128] (the reference: any d <= 128, flashAttention.cu:86;
+                                  D % 16 == 0, FA2-triton.py:177; {32,64,128} in its dispatchers); backward: d not in {32,64,128} */
   FA_B200_ERR_DTYPE = 4,       /* dtype not FA_B200_FP16 / FA_B200_BF16 */
   FA_B200_ERR_ALIGNMENT = 5,   /* base pointers must be 16-byte aligned, strides multiples of 8 elements */
   FA_B200_ERR_ARCH = 6,        /* current device is not compute capability 10.x */

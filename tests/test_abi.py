@@ -65,7 +65,7 @@ def _params(**kw):
 
 @pytest.mark.parametrize("kw,status", [
     (dict(Q=None), 1), (dict(O=None), 1), (dict(B=0), 2), (dict(N=-5), 2), (dict(N_kv=-1), 2),
-    (dict(d=48), 3), (dict(d=96), 3), (dict(d=256), 3), (dict(dtype=7), 4),
+    (dict(d=44), 3), (dict(d=0), 3), (dict(d=136), 3), (dict(d=256), 3), (dict(dtype=7), 4),
     (dict(Q=0x1008), 5), (dict(q_stride_h=8 * 1024 + 4), 5), (dict(o_stride_n=68), 5), (dict(q_stride_n=32), 2),
     (dict(stat_stride_h=64), 2),
 ])
@@ -158,7 +158,7 @@ def test_workspace_query_policy():
     n = lib.fa_b200_workspace_bytes(1, 1, 8192, 0, 64)                    # the reference's (1,1,8192,64) sweep point
     assert n > 0 and n % (8192 * (64 * 2 + 8)) == 0
     assert 2 <= n // (8192 * (64 * 2 + 8)) <= 32
-    assert lib.fa_b200_workspace_bytes(1, 1, 8192, 0, 48) == 0            # invalid shape -> 0
+    assert lib.fa_b200_workspace_bytes(1, 1, 8192, 0, 44) == 0            # invalid shape -> 0
 
 
 def test_ring_handle_validation_without_a_gpu():
@@ -170,7 +170,7 @@ def test_ring_handle_validation_without_a_gpu():
     assert lib.fa_b200_ring_create(65, 0, 1, 1, 128, 64, 0, ctypes.byref(h)) == 2
     assert lib.fa_b200_ring_create(2, 2, 1, 1, 128, 64, 0, ctypes.byref(h)) == 2          # rank
     assert lib.fa_b200_ring_create(2, 0, 1, 1, 0, 64, 0, ctypes.byref(h)) == 2            # n_local
-    assert lib.fa_b200_ring_create(2, 0, 1, 1, 128, 48, 0, ctypes.byref(h)) == 3          # head_dim
+    assert lib.fa_b200_ring_create(2, 0, 1, 1, 128, 44, 0, ctypes.byref(h)) == 3          # head_dim
     assert lib.fa_b200_ring_create(2, 0, 1, 1, 128, 64, 5, ctypes.byref(h)) == 4          # dtype
     assert not h.value
     assert lib.fa_b200_ring_forward(None, None, None, None, None, None, 0, 0.0, None) == 1

@@ -89,4 +89,4 @@ def test_work_item_rejects_bad_arguments():
     with pytest.raises(_lib.FaB200Error):
         _lib.work_item(1, 1, 128, 64, False, 5)
     with pytest.raises(_lib.FaB200Error):
-        _lib.work_item(1, 1, 128, 48, False, 0)
+        _lib.work_item(1, 1, 128, 44, False, 0)

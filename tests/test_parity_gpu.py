@@ -258,10 +258,34 @@ def test_reference_surface_entry_points(fa):
 
 def test_unsupported_head_dim_is_an_error_not_a_silent_skip(fa):
     dev = torch.device("cuda:0")
-    x = torch.zeros(1, 1, 128, 96, dtype=torch.float16, device=dev)
-    with pytest.raises(fa.FaB200Error) as e:
+    for d in (136, 256):
+        x = torch.zeros(1, 1, 128, d, dtype=torch.float16, device=dev)
+        with pytest.raises(fa.FaB200Error) as e:
+            fa.attention_forward(x, x, x)
+        assert e.value.status == 3
+    x = torch.zeros(1, 1, 128, 44, dtype=torch.float16, device=dev)      # rows of 88 bytes: not 16-byte aligned
+    with pytest.raises((fa.FaB200Error, ValueError)):
         fa.attention_forward(x, x, x)
-    assert e.value.status == 3
+
+
+@pytest.mark.parametrize("d,dtype,causal", [(16, "fp16", True), (48, "bf16", False), (80, "fp16", True), (96, "bf16", True),
+                                            (112, "fp16", False), (8, "bf16", False)])
+def test_head_dims_between_the_instantiated_sizes(fa, d, dtype, causal):
+    """Any head_dim that is a multiple of 8 up to 128 runs on the next of the 32 / 64 / 128 instantiations: TMA reads the
+    surplus columns of every box as zeros and clips them on store.  The reference's FA1 kernel takes any d <= 128
+    (flashAttention.cu:86) and its Triton path asserts D % 16 == 0 (FA2-triton.py:177); softmax scale is 1/sqrt(d) of
+    the REAL head_dim."""
+    from oracle import oracle
+    B, H, N = 2, 3, 333
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d), seeds=(81, 82, 83))
+    o, lse, l, m = _run(fa, q, k, v, _dt(dtype), causal)
+    o_ref, lse_ref, l_ref, m_ref = oracle.attention(q, k, v, causal=causal)
+    _check(o, lse, o_ref, lse_ref)
+    assert np.abs(m - m_ref).max() <= 1e-3
+    if d % 16 == 0:      # the Triton surface's own constraint: its drop-in takes the same shapes
+        tq, tk, tv = (torch.from_numpy(x).to("cuda:0", _dt(dtype)) for x in (q, k, v))
+        o2 = fa.flash_attention(tq, tk, tv, causal=causal)
+        assert np.abs(o2.float().cpu().numpy() - o_ref).max() <= O_TOL
 
 
 def test_strided_bh_views(fa):
