@@ -540,7 +540,7 @@ def ring_record(torch, dist, fa, dev, rank, world, peaks, steps, transport, barr
     if ring is not None and ring.ok:
         block = 2 * q.numel() * q.element_size()
         rec["transport"] = ("C-ABI ring (fa_b200_ring_*): copy-engine pulls from the owner's CUDA-IPC buffer, two receive "
-                            "slots, ready/ack sequence flags (cuStreamWaitValue32), no collective in the step loop")
+                            "slots, interprocess ready/pulled events + host sequence counters, no collective in the step loop")
         rec["handle_device_bytes"] = ring.device_bytes()
         rec["handle_bytes_in_kv_blocks"] = ring.device_bytes() / block
         rec["ring_traffic_bytes_per_rank_per_step"] = block
