@@ -58,6 +58,9 @@ class FaB200BwdParams(Structure):
         ("dQ", c_void_p), ("dK", c_void_p), ("dV", c_void_p), ("delta", c_void_p),
         ("B", c_int), ("H", c_int), ("N", c_int), ("d", c_int), ("dtype", c_int), ("causal", c_int),
         ("softmax_scale", c_float), ("stream", c_void_p),
+        ("N_kv", c_int),
+        ("q_stride", c_int64 * 3), ("kv_stride", c_int64 * 3), ("o_stride", c_int64 * 3), ("do_stride", c_int64 * 3),
+        ("dq_stride", c_int64 * 3), ("dkv_stride", c_int64 * 3),
     ]
 
 

@@ -215,23 +215,23 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
   return FA_B200_OK;
 }
 
-template <int D, bool kBF16, bool kCausal, bool kDQ>
-int launch_bwd(const CUtensorMap& f1, const CUtensorMap& f2, const CUtensorMap& t1, const CUtensorMap& t2,
-               const CUtensorMap& o1, const CUtensorMap& o2, const fa::BwdArgs& args, long long grid, cudaStream_t stream) {
-  auto kern = fa::fa_bwd_sm100_kernel<D, kBF16, kCausal, kDQ>;
-  constexpr int smem = fa::BwdTraits<D>::kSmemBytes;
+template <int D, bool kBF16, bool kCausal>
+int launch_bwd_dq(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
+                  const CUtensorMap& tdq, const fa::BwdArgs& args, long long grid, cudaStream_t stream) {
+  auto kern = fa::fa_bwd_dq_sm100_kernel<D, kBF16, kCausal>;
+  constexpr int smem = fa::BwdTraits<D>::kSmem2Bytes;
   static std::atomic<unsigned long long> configured{0};
   int dev = 0;
   cudaGetDevice(&dev);
   const unsigned long long bit = 1ull << (dev & 63);
   if (!(configured.load() & bit)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(bwd, smem=%d): %s", smem, cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(bwd dq, smem=%d): %s", smem, cudaGetErrorString(e));
     configured.fetch_or(bit);
   }
-  kern<<<dim3((unsigned)grid), dim3(fa::kBwdThreads), smem, stream>>>(f1, f2, t1, t2, o1, o2, args);
+  kern<<<dim3((unsigned)grid), dim3(fa::kBwdThreads), smem, stream>>>(tq, tdo, tk, tv, tdq, args);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "backward kernel launch: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "backward dQ kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1);
   return FA_B200_OK;
 }
@@ -250,30 +250,9 @@ int launch_bwd_dkdv(const CUtensorMap& tk, const CUtensorMap& tv, const CUtensor
     if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(bwd dkdv, smem=%d): %s", smem, cudaGetErrorString(e));
     configured.fetch_or(bit);
   }
-  kern<<<dim3((unsigned)grid), dim3(fa::kBwdDkdvThreads), smem, stream>>>(tk, tv, tq, tdo, tdk, tdv, args);
+  kern<<<dim3((unsigned)grid), dim3(fa::kBwdThreads), smem, stream>>>(tk, tv, tq, tdo, tdk, tdv, args);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "backward dK/dV kernel launch: %s", cudaGetErrorString(e));
-  g_launches.fetch_add(1);
-  return FA_B200_OK;
-}
-
-template <int D, bool kBF16, bool kCausal>
-int launch_bwd_dq(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
-                  const CUtensorMap& tdq, const fa::BwdArgs& args, long long grid, cudaStream_t stream) {
-  auto kern = fa::fa_bwd_dq_sm100_kernel<D, kBF16, kCausal>;
-  constexpr int smem = fa::BwdTraits<D>::kSmem2Bytes;
-  static std::atomic<unsigned long long> configured{0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (!(configured.load() & bit)) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "cudaFuncSetAttribute(bwd dq, smem=%d): %s", smem, cudaGetErrorString(e));
-    configured.fetch_or(bit);
-  }
-  kern<<<dim3((unsigned)grid), dim3(fa::kBwdDkdvThreads), smem, stream>>>(tq, tdo, tk, tv, tdq, args);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "backward dQ kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1);
   return FA_B200_OK;
 }
@@ -555,7 +534,8 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
   if (!p) return fail(FA_B200_ERR_NULL, "params is NULL");
   if (!p->Q || !p->K || !p->V || !p->O || !p->dO || !p->lse || !p->dQ || !p->dK || !p->dV || !p->delta)
     return fail(FA_B200_ERR_NULL, "backward: Q, K, V, O, dO, lse, dQ, dK, dV and delta must be non-NULL");
-  if (p->B <= 0 || p->H <= 0 || p->N <= 0) return fail(FA_B200_ERR_SHAPE, "B, H, N must be positive (got %d, %d, %d)", p->B, p->H, p->N);
+  if (p->B <= 0 || p->H <= 0 || p->N <= 0 || p->N_kv < 0)
+    return fail(FA_B200_ERR_SHAPE, "B, H, N must be positive and N_kv >= 0 (got %d, %d, %d, %d)", p->B, p->H, p->N, p->N_kv);
   const int d = p->d;
   if (d != 32 && d != 64 && d != 128) return fail(FA_B200_ERR_HEAD_DIM, "unsupported head_dim %d (supported: 32, 64, 128)", d);
   if (p->dtype != FA_B200_FP16 && p->dtype != FA_B200_BF16) return fail(FA_B200_ERR_DTYPE, "dtype must be FA_B200_FP16 or FA_B200_BF16");
@@ -563,31 +543,48 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
   for (const void* q : ptrs)
     if (reinterpret_cast<uintptr_t>(q) & 15u) return fail(FA_B200_ERR_ALIGNMENT, "backward: tensors must be 16-byte aligned");
   const long long BH = (long long)p->B * p->H;
-  const int num_tiles = (p->N + fa::kBlockM - 1) / fa::kBlockM;
-  if (BH * num_tiles > 0x7fffffffLL) return fail(FA_B200_ERR_SHAPE, "backward: too many tiles");
+  const int Nq = p->N, Nkv = p->N_kv ? p->N_kv : p->N;
+  const int q_tiles = (Nq + fa::kBlockM - 1) / fa::kBlockM, kv_tiles = (Nkv + fa::kBlockN - 1) / fa::kBlockN;
+  if (BH * std::max(q_tiles, kv_tiles) > 0x7fffffffLL) return fail(FA_B200_ERR_SHAPE, "backward: too many tiles");
+  // strides per tensor group: 0 => dense [B,H,rows,d]
+  struct Str { long long b, h, n; };
+  auto resolve = [&](const int64_t* st, long long rows) {
+    Str r;
+    r.n = st[2] ? st[2] : d;
+    r.h = st[1] ? st[1] : rows * r.n;
+    r.b = st[0] ? st[0] : (long long)p->H * r.h;
+    return r;
+  };
+  const Str qs = resolve(p->q_stride, Nq), ks = resolve(p->kv_stride, Nkv), os = resolve(p->o_stride, Nq),
+            gs = resolve(p->do_stride, Nq), dqs = resolve(p->dq_stride, Nq), dks = resolve(p->dkv_stride, Nkv);
+  for (const Str* t : {&qs, &ks, &os, &gs, &dqs, &dks}) {
+    if ((t->b % 8) || (t->h % 8) || (t->n % 8))
+      return fail(FA_B200_ERR_ALIGNMENT, "backward: batch / head / row strides must be multiples of 8 elements");
+    if (t->b <= 0 || t->h <= 0 || t->n < d)
+      return fail(FA_B200_ERR_SHAPE, "backward: strides must be positive and the row stride at least d");
+  }
   int rc = check_device();
   if (rc) return rc;
 
-  const long long sn = d, sh = (long long)p->N * d, sb = (long long)p->H * p->N * d;
   CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
-  unsigned perm = 0, perm2 = 0;
-  if ((rc = make_tmap(&tq, &perm, p->Q, p->dtype, d, p->N, p->H, p->B, sn, sh, sb))) return rc;
-  const void* bases[] = {p->K, p->V, p->dO, p->dQ, p->dK, p->dV};
-  CUtensorMap* maps[] = {&tk, &tv, &tdo, &tdq, &tdk, &tdv};
-  for (int i = 0; i < 6; ++i) {
-    if ((rc = make_tmap(maps[i], &perm2, bases[i], p->dtype, d, p->N, p->H, p->B, sn, sh, sb))) return rc;
-    if (perm2 != perm) return fail(FA_B200_ERR_DRIVER, "backward: inconsistent tensor-map axis order");
-  }
-  const float scale = (p->softmax_scale != 0.f) ? p->softmax_scale : 1.0f / sqrtf((float)d);
   fa::BwdArgs a{};
+  unsigned perm_v = 0, perm_dv = 0;
+  if ((rc = make_tmap(&tq, &a.perm_q, p->Q, p->dtype, d, Nq, p->H, p->B, qs.n, qs.h, qs.b))) return rc;
+  if ((rc = make_tmap(&tdo, &a.perm_do, p->dO, p->dtype, d, Nq, p->H, p->B, gs.n, gs.h, gs.b))) return rc;
+  if ((rc = make_tmap(&tk, &a.perm_kv, p->K, p->dtype, d, Nkv, p->H, p->B, ks.n, ks.h, ks.b))) return rc;
+  if ((rc = make_tmap(&tv, &perm_v, p->V, p->dtype, d, Nkv, p->H, p->B, ks.n, ks.h, ks.b))) return rc;
+  if ((rc = make_tmap(&tdq, &a.perm_dq, p->dQ, p->dtype, d, Nq, p->H, p->B, dqs.n, dqs.h, dqs.b))) return rc;
+  if ((rc = make_tmap(&tdk, &a.perm_dkv, p->dK, p->dtype, d, Nkv, p->H, p->B, dks.n, dks.h, dks.b))) return rc;
+  if ((rc = make_tmap(&tdv, &perm_dv, p->dV, p->dtype, d, Nkv, p->H, p->B, dks.n, dks.h, dks.b))) return rc;
+  if (perm_v != a.perm_kv || perm_dv != a.perm_dkv) return fail(FA_B200_ERR_DRIVER, "backward: inconsistent tensor-map axis order");
+  const float scale = (p->softmax_scale != 0.f) ? p->softmax_scale : 1.0f / sqrtf((float)d);
   a.lse = p->lse;
   a.delta = p->delta;
-  a.N = p->N;
-  a.H = p->H;
-  a.num_tiles = num_tiles;
+  a.Nq = Nq; a.Nkv = Nkv; a.H = p->H;
+  a.causal_off = Nkv - Nq;
+  a.q_tiles = q_tiles; a.kv_tiles = kv_tiles;
   a.scale = scale;
   a.scale_log2 = scale * 1.4426950408889634f;
-  a.perm = perm;
   const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;
   if (d >= 64) {
     a.desc_k = fa::umma_desc_hi_bits(16, 1024, 2);
@@ -605,33 +602,24 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
   const bool causal = p->causal != 0;
   // 1. delta = rowsum(dO o O)
   {
-    const long long rows = BH * p->N;
+    const long long rows = BH * Nq;
     const long long total = rows * (d / 8);
     long long blocks = std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
     if (bf16)
-      fa::bwd_delta_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)p->O, (const uint4*)p->dO, p->delta, rows, d);
+      fa::bwd_delta_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const char*)p->O, (const char*)p->dO, p->delta, rows, d, p->H,
+                                                                      Nq, os.b, os.h, os.n, gs.b, gs.h, gs.n);
     else
-      fa::bwd_delta_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)p->O, (const uint4*)p->dO, p->delta, rows, d);
+      fa::bwd_delta_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>((const char*)p->O, (const char*)p->dO, p->delta, rows, d, p->H,
+                                                                       Nq, os.b, os.h, os.n, gs.b, gs.h, gs.n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "delta kernel launch: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1);
   }
-  const long long grid = BH * num_tiles;
-  // 2. dQ kernel: fixed (Q, dO), streamed (K, V), out dQ;  3. dK/dV kernel: fixed (K, V), streamed (Q, dO), out dK (dS^T Q), dV
-#ifdef FA_BWD_DKDV_V1      // the one-tile-at-a-time dK/dV kernel of round 1 (kept for A/B measurements)
-#define FA_BWD_DKDV(D_, BF_, C_) launch_bwd<D_, BF_, C_, false>(tk, tv, tq, tdo, tdk, tdv, a, grid, stream)
-#else
-#define FA_BWD_DKDV(D_, BF_, C_) launch_bwd_dkdv<D_, BF_, C_>(tk, tv, tq, tdo, tdk, tdv, a, grid, stream)
-#endif
-#ifdef FA_BWD_DQ_V1        // the single-compute-warpgroup dQ kernel of round 1 (kept for A/B measurements)
-#define FA_BWD_DQ(D_, BF_, C_) launch_bwd<D_, BF_, C_, true>(tq, tdo, tk, tv, tdq, tdq, a, grid, stream)
-#else
-#define FA_BWD_DQ(D_, BF_, C_) launch_bwd_dq<D_, BF_, C_>(tq, tdo, tk, tv, tdq, a, grid, stream)
-#endif
-#define FA_BWD(D_, BF_, C_)                                                                 \
-  do {                                                                                      \
-    rc = FA_BWD_DQ(D_, BF_, C_);                                                            \
-    if (!rc) rc = FA_BWD_DKDV(D_, BF_, C_);                                                  \
+  // 2. dQ kernel: one CTA per (b,h,query tile);  3. dK/dV kernel: one CTA per (b,h,key tile)
+#define FA_BWD(D_, BF_, C_)                                                                               \
+  do {                                                                                                    \
+    rc = launch_bwd_dq<D_, BF_, C_>(tq, tdo, tk, tv, tdq, a, BH * q_tiles, stream);                       \
+    if (!rc) rc = launch_bwd_dkdv<D_, BF_, C_>(tk, tv, tq, tdo, tdk, tdv, a, BH * kv_tiles, stream);      \
   } while (0)
   if (d == 128) {
     if (bf16) { if (causal) FA_BWD(128, true, true); else FA_BWD(128, true, false); }
@@ -644,8 +632,6 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
     else      { if (causal) FA_BWD(64, false, true); else FA_BWD(64, false, false); }
   }
 #undef FA_BWD
-#undef FA_BWD_DKDV
-#undef FA_BWD_DQ
   return rc;
 }
 

@@ -65,21 +65,16 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
         raise TypeError("q, k, v must share a dtype")
     dtype = _dtype_code(q)
 
-    def tma_ok(t: torch.Tensor) -> bool:
-        # what a TMA descriptor can address: d contiguous, every other stride a positive multiple of 8 elements.
-        # Stride 0 (a broadcast view such as k.expand(B, H, N, d) for GQA/MQA) is NOT expressible: the C ABI
-        # reads 0 as "dense default", so such a view must never reach it as is.
-        return t.stride(3) == 1 and all(t.shape[i] == 1 or (t.stride(i) > 0 and t.stride(i) % 8 == 0) for i in range(3))
-
+    # Stride 0 (a broadcast view such as k.expand(B, H, N, d) for GQA/MQA) is NOT expressible to TMA, and the C ABI
+    # reads 0 as "dense default", so such a view must never reach it as is (see _tma_ok).
     # inputs the descriptors cannot address are copied (broadcast heads, odd strides); outputs must be addressable
-    q, k, v = (t if tma_ok(t) else t.contiguous() for t in (q, k, v))
+    q, k, v = (t if _tma_ok(t) else t.contiguous() for t in (q, k, v))
 
     def strides(t: torch.Tensor, what: str):
-        if not tma_ok(t):
+        if not _tma_ok(t):
             raise ValueError(f"{what}: needs a contiguous last dimension and batch/head/row strides that are positive "
                              "multiples of 8 elements")
-        # size-1 axes report arbitrary strides in torch: give the kernel the dense default (0) for those
-        return tuple(t.stride(i) if t.shape[i] > 1 else 0 for i in range(3))
+        return _strides3(t)
 
     qs, ks, vs = strides(q, "q"), strides(k, "k"), strides(v, "v")
     if ks != vs:      # K and V share one set of strides in the ABI
@@ -131,28 +126,57 @@ def attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, caus
     return out, lse
 
 
+def _tma_ok(t: torch.Tensor) -> bool:
+    """What a TMA descriptor can address: d contiguous, every other stride a positive multiple of 8 elements."""
+    return t.stride(3) == 1 and all(t.shape[i] == 1 or (t.stride(i) > 0 and t.stride(i) % 8 == 0) for i in range(3))
+
+
+def _strides3(t: torch.Tensor):
+    # size-1 axes report arbitrary strides in torch: give the kernel the dense default (0) for those
+    return tuple(t.stride(i) if t.shape[i] > 1 else 0 for i in range(3))
+
+
 def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor,
                        do: torch.Tensor, *, causal: bool = False, softmax_scale: Optional[float] = None):
     """(dQ, dK, dV) of O = softmax(Q K^T scale [+ causal mask]) V for the upstream gradient `do`, from the forward's
-    output `o` and logsumexp `lse` (reference: FA2-triton.py:98-170).  Dense [B,H,N,d]
-    fp16/bf16 CUDA tensors with N_kv == N; three launches of libfa_b200.so (fa_b200_backward), no atomics."""
+    output `o` and logsumexp `lse` (reference: FA2-triton.py:98-170, :207-237).
+
+    q, o, do: [B,H,N,d]; k, v: [B,H,N_kv,d]; fp16/bf16 CUDA tensors, d in {32, 64, 128}.  As in the reference's backward
+    (which hands every tensor's strides to its kernel) batch / head / row strides are free: views such as
+    `x.transpose(1, 2)` of [B,N,H,d] storage go to the kernels' TMA descriptors as they are; only views a descriptor
+    cannot address (stride 0, strides that are not multiples of 8) are copied first.  The gradients come back dense.
+    Three launches of libfa_b200.so (fa_b200_backward), no atomics."""
     _require_cuda(q, k, v, o, lse, do)
     B, H, N, d = q.shape
+    Nkv = k.shape[2]
+    if k.shape != (B, H, Nkv, d) or v.shape != k.shape:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)}")
+    for t_, name in ((o, "o"), (do, "do")):
+        if t_.shape != q.shape:
+            raise ValueError(f"{name} must have q's shape")
     for t_, name in ((k, "k"), (v, "v"), (o, "o"), (do, "do")):
-        if t_.shape != q.shape or t_.dtype != q.dtype:
-            raise ValueError(f"{name} must have q's shape and dtype (backward supports N_kv == N only)")
+        if t_.dtype != q.dtype:
+            raise TypeError(f"{name} must have q's dtype")
     if lse.shape != (B, H, N) or lse.dtype != torch.float32:
         raise ValueError("lse must be fp32 [B,H,N]")
-    q, k, v, o, do, lse = (t_.contiguous() for t_ in (q, k, v, o, do, lse))
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    q, k, v, o, do = (t_ if _tma_ok(t_) else t_.contiguous() for t_ in (q, k, v, o, do))
+    if _strides3(k) != _strides3(v):      # K and V share one set of strides in the ABI
+        k, v = k.contiguous(), v.contiguous()
+    lse = lse.contiguous()
+    dq, dk, dv = torch.empty_like(q, memory_format=torch.contiguous_format), \
+        torch.empty_like(k, memory_format=torch.contiguous_format), torch.empty_like(v, memory_format=torch.contiguous_format)
     delta = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
     p = _lib.FaB200BwdParams()
     p.Q, p.K, p.V, p.O, p.dO, p.lse = (t_.data_ptr() for t_ in (q, k, v, o, do, lse))
     p.dQ, p.dK, p.dV, p.delta = dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr()
     p.B, p.H, p.N, p.d = B, H, N, d
+    p.N_kv = 0 if Nkv == N else Nkv
     p.dtype = _dtype_code(q)
     p.causal = 1 if causal else 0
     p.softmax_scale = float(softmax_scale) if softmax_scale else 0.0
+    for name, t_ in (("q_stride", q), ("kv_stride", k), ("o_stride", o), ("do_stride", do)):
+        for i, s_ in enumerate(_strides3(t_)):
+            getattr(p, name)[i] = s_
     p.stream = _stream_ptr(q)
     with torch.cuda.device(q.device):
         _lib.check(_lib.load().fa_b200_backward(ctypes.byref(p)))
@@ -165,7 +189,6 @@ class FlashAttnFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, causal: bool):
-        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         o, lse = attention_forward(q, k, v, causal=causal)
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.causal = causal
@@ -174,7 +197,7 @@ class FlashAttnFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv = attention_backward(q, k, v, o, lse, do.contiguous(), causal=ctx.causal)
+        dq, dk, dv = attention_backward(q, k, v, o, lse, do, causal=ctx.causal)
         return dq, dk, dv, None
 
 

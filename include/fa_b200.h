@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define FA_B200_VERSION_MAJOR 0
-#define FA_B200_VERSION_MINOR 5
+#define FA_B200_VERSION_MINOR 6
 
 /* status codes (0 = ok).  The reference returns void and prints to stderr
  * (flash_attn_cutlass.cu:540-542, :510-514); the C ABI returns codes instead. */
@@ -141,20 +141,22 @@ int fa_b200_cast_output(void* O, const float* O_acc, int64_t rows, int d, int dt
 
 /* ---- backward (reference: code/triton_fa2/FA2-triton.py:98-170, :207-237) ---------------------
  * dQ, dK, dV of O = softmax(Q K^T scale [+ causal mask]) V for an upstream gradient dO, from the forward's O and
- * logsumexp (for the reference's saved statistics: lse = m + ln l, FA2-triton.py:203).  Dense [B,H,N,d] tensors, N_kv == N.
+ * logsumexp (for the reference's saved statistics: lse = m + ln l, FA2-triton.py:203).  Q, O, dO, dQ are [B,H,N,d] and
+ * K, V, dK, dV [B,H,N_kv,d] views with free batch / head / row strides, as the reference's backward takes them
+ * (`q.stride(i)` ... `dV.stride(i)`, FA2-triton.py:219-227); the causal mask is the forward's (col > row + N_kv - N).
  * Three launches: delta = rowsum(dO o O) (HBM-bound), a dQ kernel and a dK/dV kernel (tcgen05; see
  * flash_attention_impls_b200/csrc/fa_bwd_sm100.cuh).  Every output element has one writer: no atomics (the reference
  * accumulates dK/dV with fp16 atomic adds, :164-167), deterministic, outputs are overwritten, not accumulated into.
- * `delta` is caller-provided fp32 scratch of B*H*N elements. */
+ * `delta` is caller-provided fp32 scratch of B*H*N elements; lse and delta are dense [B,H,N].  d in {32, 64, 128}. */
 typedef struct fa_b200_bwd_params {
   const void* Q;     /* [B,H,N,d] dtype */
-  const void* K;
+  const void* K;     /* [B,H,N_kv,d] */
   const void* V;
   const void* O;     /* forward output */
-  const void* dO;    /* upstream gradient, same layout */
-  const float* lse;  /* [B,H,N] forward logsumexp */
+  const void* dO;    /* upstream gradient */
+  const float* lse;  /* [B,H,N] forward logsumexp (-inf for a row that saw no key) */
   void* dQ;          /* [B,H,N,d] dtype, written */
-  void* dK;
+  void* dK;          /* [B,H,N_kv,d] dtype, written */
   void* dV;
   float* delta;      /* [B,H,N] fp32 scratch */
   int B, H, N, d;
@@ -162,6 +164,15 @@ typedef struct fa_b200_bwd_params {
   int causal;
   float softmax_scale; /* 0 => 1/sqrt(d) */
   void* stream;
+  /* ---- everything below may stay zero: dense tensors, N_kv == N (the only case version 0.4 had) */
+  int N_kv;          /* 0 => N */
+  /* element strides {batch, head, row} per tensor group, 0 => the dense default; d is contiguous; multiples of 8 */
+  int64_t q_stride[3];     /* Q */
+  int64_t kv_stride[3];    /* K and V */
+  int64_t o_stride[3];     /* O */
+  int64_t do_stride[3];    /* dO */
+  int64_t dq_stride[3];    /* dQ */
+  int64_t dkv_stride[3];   /* dK and dV */
 } fa_b200_bwd_params;
 int fa_b200_backward(const fa_b200_bwd_params* p);
 

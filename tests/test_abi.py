@@ -48,7 +48,7 @@ def test_struct_layout_matches_header():
 
 def test_version_and_status_strings():
     lib = _lib.load()
-    assert lib.fa_b200_version() == (0 << 16) | 5
+    assert lib.fa_b200_version() == (0 << 16) | 6
     assert lib.fa_b200_status_string(0) == b"ok"
     assert lib.fa_b200_status_string(3) == b"unsupported head_dim"
     assert lib.fa_b200_status_string(99) == b"unknown status"
@@ -118,8 +118,15 @@ def test_backward_validation_returns_codes_without_a_gpu():
     assert lib.fa_b200_backward(ctypes.byref(p)) == 4
     p.dtype, p.dO = 0, 0x1004
     assert lib.fa_b200_backward(ctypes.byref(p)) == 5
-    # 10 pointers, 6 ints + float (+ padding), stream
-    assert ctypes.sizeof(_lib.FaB200BwdParams) == 10 * 8 + 8 * 4 + 8
+    p.dO, p.N_kv = 0x1000, -3
+    assert lib.fa_b200_backward(ctypes.byref(p)) == 2
+    p.N_kv = 0
+    p.do_stride[2] = 68
+    assert lib.fa_b200_backward(ctypes.byref(p)) == 5          # stride not a multiple of 8
+    p.do_stride[2] = 32
+    assert lib.fa_b200_backward(ctypes.byref(p)) == 2          # row stride smaller than d
+    # 10 pointers, 6 ints + float (+ padding), stream, N_kv (+ padding), 6 x 3 strides
+    assert ctypes.sizeof(_lib.FaB200BwdParams) == 10 * 8 + 8 * 4 + 8 + 8 + 18 * 8
 
 
 def test_precise_flag_is_part_of_the_parameter_block():

@@ -166,3 +166,62 @@ def test_full_size_c4_backward_against_oracle(fa):
     qs, ks, vs, dos, os_, ls_ = (t[1:2, 5:9].contiguous() for t in (q, k, v, do, o, lse))
     dq2, dk2, dv2 = fa.attention_backward(qs, ks, vs, os_, ls_, dos, causal=True)
     assert torch.equal(dq2, dq[1:2, 5:9]) and torch.equal(dk2, dk[1:2, 5:9]) and torch.equal(dv2, dv[1:2, 5:9])
+
+
+@pytest.mark.parametrize("B,H,N,Nkv,d,dtype,causal", [
+    (1, 2, 300, 500, 64, torch.float16, False),      # N_kv > N
+    (2, 2, 500, 300, 128, torch.bfloat16, False),    # N_kv < N
+    (1, 3, 300, 500, 128, torch.bfloat16, True),     # causal, bottom-right aligned: every query sees >= 201 keys
+    (1, 2, 500, 300, 64, torch.float16, True),       # causal with N_kv < N: the first 200 queries see NO key (lse = -inf)
+    (1, 2, 128, 700, 32, torch.bfloat16, True),      # one query tile against many key tiles
+    (1, 2, 700, 128, 128, torch.float16, True),      # many query tiles, one key tile; query tiles 0..3 see nothing
+])
+def test_backward_with_a_different_number_of_keys(fa, B, H, N, Nkv, d, dtype, causal):
+    """N_kv != N with the forward's mask rule col > row + (N_kv - N): whole tiles that see nothing get zero gradients,
+    rows with lse = -inf contribute nothing."""
+    from oracle import oracle
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, Nkv, d), seeds=(91, 92, 93))
+    do, _, _ = oracle.set_s((B, H, N, d), (B, H, N, d), seeds=(94, 95, 96))
+    dev = torch.device("cuda:0")
+    tq, tk, tv, tdo = (torch.from_numpy(x).to(dev, dtype) for x in (q, k, v, do))
+    o, lse = fa.attention_forward(tq, tk, tv, causal=causal)
+    dq, dk, dv = fa.attention_backward(tq, tk, tv, o, lse, tdo, causal=causal)
+    torch.cuda.synchronize()
+    rq, rk, rv, _ = oracle.attention_backward_f64(q, k, v, do, causal=causal)
+    for got, ref in ((dq, rq), (dk, rk), (dv, rv)):
+        assert torch.isfinite(got.float()).all()
+        assert _rel(got, ref) <= TOL[dtype]
+    if causal and Nkv < N:      # queries that see no key: exactly zero dQ rows
+        assert torch.all(dq[:, :, :N - Nkv] == 0)
+
+
+@pytest.mark.parametrize("d,dtype,causal", [(128, torch.bfloat16, True), (64, torch.float16, False)])
+def test_backward_takes_strided_views_without_copies(fa, d, dtype, causal):
+    """[B,N,H,d] storage viewed as [B,H,N,d] (row stride H*d, head stride d) for q, k, v, o and do - what the
+    reference's backward accepts through `x.stride(i)` (FA2-triton.py:219-227) - gives bit-identical gradients to
+    the dense layout, and goes through the autograd mirror as well."""
+    from oracle import oracle
+    B, H, N = 2, 3, 400
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d), seeds=(101, 102, 103))
+    do, _, _ = oracle.set_s((B, H, N, d), (B, H, N, d), seeds=(104, 105, 106))
+    dev = torch.device("cuda:0")
+    dense = [torch.from_numpy(x).to(dev, dtype) for x in (q, k, v, do)]
+    views = [t.transpose(1, 2).contiguous().transpose(1, 2) for t in dense]       # same values, [B,N,H,d] storage
+    assert not views[0].is_contiguous()
+    o_d, lse_d = fa.attention_forward(dense[0], dense[1], dense[2], causal=causal)
+    o_v = torch.empty((B, N, H, d), dtype=dtype, device=dev).transpose(1, 2)
+    fa.attention_forward(views[0], views[1], views[2], causal=causal, out=o_v, lse=lse_d.clone())
+    g_d = fa.attention_backward(dense[0], dense[1], dense[2], o_d, lse_d, dense[3], causal=causal)
+    g_v = fa.attention_backward(views[0], views[1], views[2], o_v, lse_d, views[3], causal=causal)
+    torch.cuda.synchronize()
+    for a_, b_ in zip(g_d, g_v):
+        assert torch.equal(a_, b_)
+    rq, rk, rv, _ = oracle.attention_backward_f64(q, k, v, do, causal=causal)
+    for got, ref in zip(g_v, (rq, rk, rv)):
+        assert _rel(got, ref) <= TOL[dtype]
+    # autograd on strided leaves
+    leaves = [t.clone().requires_grad_(True) for t in views[:3]]
+    out = fa.flash_attention(leaves[0], leaves[1], leaves[2], causal=causal)
+    out.backward(views[3])
+    for leaf, ref in zip(leaves, g_d):
+        assert torch.equal(leaf.grad, ref)
