@@ -605,12 +605,14 @@ int fa_b200_backward(const fa_b200_bwd_params* p) {
     const long long rows = BH * Nq;
     const long long total = rows * (d / 8);
     long long blocks = std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
-    if (bf16)
-      fa::bwd_delta_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const char*)p->O, (const char*)p->dO, p->delta, rows, d, p->H,
-                                                                      Nq, os.b, os.h, os.n, gs.b, gs.h, gs.n);
-    else
-      fa::bwd_delta_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>((const char*)p->O, (const char*)p->dO, p->delta, rows, d, p->H,
-                                                                       Nq, os.b, os.h, os.n, gs.b, gs.h, gs.n);
+    auto is_dense = [&](const Str& t) { return t.n == d && t.h == (long long)Nq * d && t.b == (long long)p->H * Nq * d; };
+    const bool dense = is_dense(os) && is_dense(gs);
+#define FA_DELTA(BF_, DN_)                                                                                          \
+  fa::bwd_delta_kernel<BF_, DN_><<<(unsigned)blocks, 256, 0, stream>>>((const char*)p->O, (const char*)p->dO, p->delta, rows, d, \
+                                                                       p->H, Nq, os.b, os.h, os.n, gs.b, gs.h, gs.n)
+    if (bf16) { if (dense) FA_DELTA(true, true); else FA_DELTA(true, false); }
+    else      { if (dense) FA_DELTA(false, true); else FA_DELTA(false, false); }
+#undef FA_DELTA
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "delta kernel launch: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1);

@@ -62,8 +62,9 @@ struct BwdTraits {
 };
 
 // delta[row] = sum_t dO[row,t] * O[row,t]  (fp32), row = (b*H + h)*N + n.  One thread per 8 elements, d/8 lanes per
-// row; O and dO are [B,H,N,d] views with element strides (sb, sh, sn).
-template <bool kBF16>
+// row; O and dO are [B,H,N,d] views with element strides (sb, sh, sn); kDense: both are dense, so the row / head /
+// batch decomposition (64-bit divisions) is skipped and the tensors are read as plain 16-byte streams.
+template <bool kBF16, bool kDense>
 __global__ void __launch_bounds__(256)
 bwd_delta_kernel(const char* __restrict__ O, const char* __restrict__ dO, float* __restrict__ delta, long long rows, int d,
                  int H, int N, long long o_sb, long long o_sh, long long o_sn, long long do_sb, long long do_sh,
@@ -76,12 +77,18 @@ bwd_delta_kernel(const char* __restrict__ O, const char* __restrict__ dO, float*
     const long long idx = base + threadIdx.x;
     float s = 0.f;
     if (idx < total) {
-      const long long row = idx / lanes;
-      const int v = int(idx - row * lanes);
-      const long long bh = row / N, n = row - bh * N;
-      const long long b = bh / H, h = bh - b * H;
-      const uint4 a = *reinterpret_cast<const uint4*>(O + (b * o_sb + h * o_sh + n * o_sn + v * 8) * 2);
-      const uint4 g = *reinterpret_cast<const uint4*>(dO + (b * do_sb + h * do_sh + n * do_sn + v * 8) * 2);
+      uint4 a, g;
+      if constexpr (kDense) {
+        a = reinterpret_cast<const uint4*>(O)[idx];
+        g = reinterpret_cast<const uint4*>(dO)[idx];
+      } else {
+        const long long row = idx / lanes;
+        const int v = int(idx - row * lanes);
+        const long long bh = row / N, n = row - bh * N;
+        const long long b = bh / H, h = bh - b * H;
+        a = *reinterpret_cast<const uint4*>(O + (b * o_sb + h * o_sh + n * o_sn + v * 8) * 2);
+        g = *reinterpret_cast<const uint4*>(dO + (b * do_sb + h * do_sh + n * do_sn + v * 8) * 2);
+      }
       const float2 a0 = unpack2<kBF16>(a.x), a1 = unpack2<kBF16>(a.y), a2 = unpack2<kBF16>(a.z), a3 = unpack2<kBF16>(a.w);
       const float2 b0 = unpack2<kBF16>(g.x), b1 = unpack2<kBF16>(g.y), b2 = unpack2<kBF16>(g.z), b3 = unpack2<kBF16>(g.w);
       s = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;

@@ -6,10 +6,12 @@ multi-GPU code at all; both modes are new work named by BASELINE.json's north_st
 * ring attention — the sequence is split over the ranks; each rank runs the local kernel on one K/V block
   at a time, in ring order (step s uses the block of rank r-s); every step writes its partial (O_s, lse_s) into
   slot s of a stacked buffer and ONE pass at the end merges the P partials with their logsumexp (2 bytes read per
-  element and partial, instead of a 10-byte read-modify-write of an fp32 accumulator after every step).  The blocks travel over NVLink/NVSwitch in one of two ways: `transport="peer"` (default on a
-  single node): every rank publishes its block in a CUDA-IPC buffer and the others PULL it with the copy
-  engines, which needs no SM; `transport="p2p"`: NCCL send/recv through torch.distributed (also what the CPU/gloo
-  tests of the schedule use).  Causal runs use the zig-zag partition (rank r owns
+  element and partial, instead of a 10-byte read-modify-write of an fp32 accumulator after every step).  The blocks
+  travel over NVLink/NVSwitch in one of two ways: `transport="peer"` (default on a single node): the C-ABI ring
+  (`fa_b200_ring_*`, csrc/fa_ring.cu) - every rank publishes its block in a CUDA-IPC buffer and the others PULL it
+  with the copy engines through a window of two receive slots, ordered by interprocess events, which needs no SM
+  and no collective; `transport="p2p"`: NCCL send/recv through torch.distributed (also what the CPU/gloo tests of the
+  schedule use).  Causal runs use the zig-zag partition (rank r owns
   sequence chunks r and 2P-1-r) so that every rank does the same amount of work at every step.
 
 One process per GPU; the compute calls go to libfa_b200.so through `ops`.  The `backend` argument
@@ -118,8 +120,9 @@ class _CRing:
     ranks talk on the host: every rank creates its handle, and ONE all-gather carries (hostname, status, 128-byte
     export blob), so that all ranks take the same decision - the peer transport is used only when every rank sits
     on the same host and every create and every connect succeeded; otherwise every rank destroys its handle and the
-    group falls back to NCCL send/recv.  After that a forward is enqueue-only: copy-engine pulls through a window of
-    two receive slots, ordered by sequence flags in the mapped memory (no collective, no host synchronisation)."""
+    group falls back to NCCL send/recv.  After that a forward is enqueue-only on the device: copy-engine pulls through
+    a window of two receive slots, ordered by interprocess events (no collective; the hosts only exchange sequence
+    counters through shared memory)."""
 
     def __init__(self, shape, dtype, group, device):
         import ctypes
