@@ -23,6 +23,9 @@
 #include "fa_bwd_sm100.cuh"
 
 namespace fa {
+int launch_item_combine(const void* O_part, const float* lse_part, const float* m_part, void* O, float* lse, float* l, float* m,
+                        const FwdArgs& a, int d, long long o_sb, long long o_sh, long long o_sn, long long st_sb, long long st_sh,
+                        int dtype, bool causal, cudaStream_t stream);
 int launch_split_combine(const void* O_part, const float* lse_part, const float* m_part, void* O, float* lse,
                          float* l, float* m, int nsplit, long long rows, int d, int H, int N, long long o_sb,
                          long long o_sh, long long o_sn, long long st_sb, long long st_sh, int dtype,
@@ -165,7 +168,7 @@ int check_device() {
 
 
 template <int D, bool kBF16, bool kCausal, bool kPrecise>
-int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, const CUtensorMap& tw,
            const fa::FwdArgs& args, long long grid, cudaStream_t stream) {
   auto kern = fa::fa_fwd_sm100_kernel<D, kBF16, kCausal, kPrecise>;
   constexpr int smem = fa::FwdTraits<D>::kSmemBytes;
@@ -190,7 +193,7 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
     cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(long long), stream);
     targs.trace = trace_dev;
   }
-  kern<<<dim3((unsigned)grid), dim3(fa::kNumThreads), smem, stream>>>(tq, tk, tv, to, targs);
+  kern<<<dim3((unsigned)grid), dim3(fa::kNumThreads), smem, stream>>>(tq, tk, tv, to, tw, targs);
   if (trace_path) {
     static long long h[4096 + 160 * 40 * 2];
     cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
@@ -207,7 +210,7 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
     }
   }
 #else
-  kern<<<dim3((unsigned)grid), dim3(fa::kNumThreads), smem, stream>>>(tq, tk, tv, to, args);
+  kern<<<dim3((unsigned)grid), dim3(fa::kNumThreads), smem, stream>>>(tq, tk, tv, to, tw, args);
 #endif
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(FA_B200_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
@@ -257,15 +260,6 @@ int launch_bwd_dkdv(const CUtensorMap& tk, const CUtensorMap& tv, const CUtensor
   return FA_B200_OK;
 }
 
-// Bring-up overrides (UMMA descriptors, split count) exist only in -DFA_B200_DEBUG builds: a stray environment
-// variable must not be able to corrupt a descriptor in the shipped library.
-#ifdef FA_B200_DEBUG
-unsigned long long env_u64(const char* name, unsigned long long dflt) {
-  const char* s = getenv(name);
-  return s ? strtoull(s, nullptr, 0) : dflt;
-}
-#endif
-
 // FA_B200_GROUP_HEADS (tuning knob of the causal item order; 0 = the L2-sized default) is read once per process.
 std::atomic<long long> g_group_heads{-1};   // -1: not initialised yet
 long long group_heads_override() {
@@ -278,20 +272,48 @@ long long group_heads_override() {
   return v;
 }
 
-// Split-KV policy: how many key-axis splits for a launch with `items` work items of `n_kv_tiles` K/V tiles each.
-int choose_nsplit(long long items, int n_kv_tiles, int sms) {
-  if (items * 2 > sms || n_kv_tiles < 8) return 1;          // enough parallelism already, or too short to split
-  long long n = sms / items;                                 // fill the machine once
-  n = std::min<long long>(n, n_kv_tiles / 4);                // at least 4 tiles per split
-  n = std::min<long long>(n, 32);
+// Bring-up overrides (UMMA descriptors, split count) exist only in -DFA_B200_DEBUG builds: a stray environment
+// variable must not be able to corrupt a descriptor in the shipped library.
+#ifdef FA_B200_DEBUG
+unsigned long long env_u64(const char* name, unsigned long long dflt) {
+  const char* s = getenv(name);
+  return s ? strtoull(s, nullptr, 0) : dflt;
+}
+#endif
+
+// Split-KV policy for a launch of `items` work items of `n_kv_tiles` K/V tiles each.  Returns the number of key-axis
+// splits and sets *split_begin to the list position from which items are split:
+//   * far fewer items than SMs (the reference's (1,1,N,64) sweep): every item is split so the machine fills once;
+//   * non-causal launches of equal items whose last wave fills at most half of the SMs (512 items on 148 SMs = 3.46
+//     waves: c3 sharded over 8 GPUs, 0.433 -> 0.406 ms) and whose items are at least 24 K/V tiles long: only that tail
+//     is split, so it costs 1/nsplit of a round instead of a whole one.  (Causal items are ordered longest-first, their
+//     tail is short already; at BASELINE c2's 8 tiles per item the combine launch costs more than the split saves:
+//     0.0661 -> 0.0680 ms, profiles/r02_tail_split.log.)
+int choose_nsplit(long long items, int n_kv_tiles, int sms, bool causal, long long* split_begin) {
+  *split_begin = 0;
+  long long n = 1;
+  if (n_kv_tiles >= 8) {
+    if (items * 2 <= sms) {
+      n = std::min<long long>(std::min<long long>(sms / items, n_kv_tiles / 4), 32);   // >= 4 tiles per split
+    } else if (!causal && items > sms && n_kv_tiles >= 24) {   // shorter items: the combine launch costs what the split saves
+      const long long tail = items % sms;
+      if (tail > 0 && tail * 2 <= sms) {
+        n = std::min<long long>(std::min<long long>(sms / tail, n_kv_tiles / 4), 8);
+        if (n > 1) *split_begin = items - tail;
+      }
+    }
+  }
 #ifdef FA_B200_DEBUG
   n = (long long)env_u64("FA_B200_NSPLIT", (unsigned long long)n);
 #endif
-  return (int)std::max<long long>(1, std::min<long long>(n, n_kv_tiles));
+  n = std::max<long long>(1, std::min<long long>(n, n_kv_tiles));
+  if (n == 1) *split_begin = 0;
+  return (int)n;
 }
 
-size_t split_workspace_bytes(int nsplit, long long rows, int d) {
-  return nsplit <= 1 ? 0 : (size_t)nsplit * rows * ((size_t)d * 2 + 2 * sizeof(float));
+// partial O (16-bit) + lse + m for `ws_items` items of 256 rows, `nsplit` times
+size_t split_workspace_bytes(int nsplit, long long ws_items, int d) {
+  return nsplit <= 1 ? 0 : (size_t)nsplit * ws_items * 2 * fa::kBlockM * ((size_t)d * 2 + 2 * sizeof(float));
 }
 
 // SMs of the current device (queried once per device; 148 on B200, which is also the answer when no device is
@@ -324,16 +346,19 @@ void fill_schedule(fa::FwdArgs& a, long long BH, int Nq, int Nkv, int d) {
   if (group_heads_override() > 0) g = group_heads_override();
   a.group_heads = (int)std::max<long long>(1, std::min<long long>(g, BH));
   a.nsplit = 1;
+  a.split_begin = 0;
+  a.num_ws_items = 0;
   a.tiles_per_split = (Nkv + fa::kBlockN - 1) / fa::kBlockN;
 }
 
-// Switch the schedule to `nsplit` key-axis splits.
-void apply_split(fa::FwdArgs& a, int nsplit, int B) {
+// Switch the schedule to `nsplit` key-axis splits of the items from list position `split_begin` on.
+void apply_split(fa::FwdArgs& a, int nsplit, long long split_begin) {
   const int n_kv_tiles = (a.Nkv + fa::kBlockN - 1) / fa::kBlockN;
   a.nsplit = nsplit;
   a.tiles_per_split = (n_kv_tiles + nsplit - 1) / nsplit;
-  a.num_items *= nsplit;
-  a.B = B;
+  a.split_begin = (int)split_begin;
+  a.num_ws_items = a.num_items - (int)split_begin;
+  a.num_items = (int)split_begin + a.num_ws_items * nsplit;
 }
 
 }  // namespace
@@ -364,8 +389,11 @@ size_t fa_b200_workspace_bytes(int B, int H, int N, int N_kv, int d) {
   if (B <= 0 || H <= 0 || N <= 0 || N_kv < 0 || d < 8 || d > 128 || (d % 8)) return 0;
   const int Nkv = N_kv ? N_kv : N;
   const long long items = (long long)B * H * ((N + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM));
-  const int nsplit = choose_nsplit(items, (Nkv + fa::kBlockN - 1) / fa::kBlockN, sm_count());
-  return split_workspace_bytes(nsplit, (long long)B * H * N, d);
+  // the causal flag is not an argument: report the larger (non-causal) need, which also covers the causal policy
+  long long sb_nc = 0, sb_c = 0;
+  const int n_nc = choose_nsplit(items, (Nkv + fa::kBlockN - 1) / fa::kBlockN, sm_count(), false, &sb_nc);
+  const int n_c = choose_nsplit(items, (Nkv + fa::kBlockN - 1) / fa::kBlockN, sm_count(), true, &sb_c);
+  return std::max(split_workspace_bytes(n_nc, items - sb_nc, d), split_workspace_bytes(n_c, items - sb_c, d));
 }
 
 int fa_b200_forward(const fa_b200_params* p) {
@@ -414,26 +442,28 @@ int fa_b200_forward(const fa_b200_params* p) {
   if (rc) return rc;
 
   // split-KV: only with a large enough caller-provided workspace
-  const long long rows_total = BH * Nq;
-  int nsplit = choose_nsplit(BH * num_q_blocks, (Nkv + fa::kBlockN - 1) / fa::kBlockN, sm_count());
-  if (nsplit > 1 && (!p->workspace || p->workspace_bytes < split_workspace_bytes(nsplit, rows_total, d) ||
+  long long split_begin = 0;
+  int nsplit = choose_nsplit(BH * num_q_blocks, (Nkv + fa::kBlockN - 1) / fa::kBlockN, sm_count(), p->causal != 0, &split_begin);
+  const long long ws_items = BH * num_q_blocks - split_begin;
+  if (nsplit > 1 && (!p->workspace || p->workspace_bytes < split_workspace_bytes(nsplit, ws_items, d) ||
                      (reinterpret_cast<uintptr_t>(p->workspace) & 15u)))
     nsplit = 1;
+  const long long ws_rows = ws_items * 2 * fa::kBlockM;     // rows of one split's partial
   char* ws_o = static_cast<char*>(p->workspace);
-  float* ws_lse = nsplit > 1 ? reinterpret_cast<float*>(ws_o + (size_t)nsplit * rows_total * d * 2) : nullptr;
-  float* ws_m = nsplit > 1 ? ws_lse + (size_t)nsplit * rows_total : nullptr;
+  float* ws_lse = nsplit > 1 ? reinterpret_cast<float*>(ws_o + (size_t)nsplit * ws_rows * d * 2) : nullptr;
+  float* ws_m = nsplit > 1 ? ws_lse + (size_t)nsplit * ws_rows : nullptr;
 
-  CUtensorMap tq, tk, tv, to;
-  unsigned perm_q = 0, perm_kv = 0, perm_v = 0, perm_o = 0;
+  CUtensorMap tq, tk, tv, to, tw;
+  unsigned perm_q = 0, perm_kv = 0, perm_v = 0, perm_o = 0, perm_w = 0;
   if ((rc = make_tmap(&tq, &perm_q, p->Q, p->dtype, d, Nq, p->H, p->B, qs.n, qs.h, qs.b))) return rc;
   if ((rc = make_tmap(&tk, &perm_kv, p->K, p->dtype, d, Nkv, p->H, p->B, ks.n, ks.h, ks.b))) return rc;
   if ((rc = make_tmap(&tv, &perm_v, p->V, p->dtype, d, Nkv, p->H, p->B, ks.n, ks.h, ks.b))) return rc;
-  if (nsplit > 1) {   // partial O goes to the dense workspace [nsplit*B, H, N, d]
-    if ((rc = make_tmap(&to, &perm_o, ws_o, p->dtype, d, Nq, p->H, (long long)nsplit * p->B, d, (long long)Nq * d,
-                        (long long)p->H * Nq * d)))
+  if ((rc = make_tmap(&to, &perm_o, p->O, p->dtype, d, Nq, p->H, p->B, os.n, os.h, os.b))) return rc;
+  if (nsplit > 1) {   // partials go to the workspace, laid out by item: [nsplit][ws_items][256 rows][d]
+    if ((rc = make_tmap(&tw, &perm_w, ws_o, p->dtype, d, 2 * fa::kBlockM, ws_items, nsplit, d, 2LL * fa::kBlockM * d, ws_rows * d)))
       return rc;
-  } else if ((rc = make_tmap(&to, &perm_o, p->O, p->dtype, d, Nq, p->H, p->B, os.n, os.h, os.b))) {
-    return rc;
+  } else {
+    tw = to;
   }
 
   const float scale = (p->softmax_scale != 0.f) ? p->softmax_scale : 1.0f / sqrtf((float)d);
@@ -443,12 +473,14 @@ int fa_b200_forward(const fa_b200_params* p) {
   a.m = p->m;
   fill_schedule(a, BH, Nq, Nkv, d);
   a.scale_log2 = scale * 1.4426950408889634f;
+  a.need_stats = (p->l || p->m) ? 1 : 0;   // l / m need the exact row max of every tile (no fast softmax path)
   a.stat_stride_b = ssb;
   a.stat_stride_h = ssh;
   a.H = p->H;
   a.perm_q = perm_q;
   a.perm_kv = perm_kv;
   a.perm_o = perm_o;
+  a.perm_w = perm_w;
   const unsigned fmt = (p->dtype == FA_B200_BF16) ? 1u : 0u;
   if (dk >= 64) {
     // Q, K: K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.
@@ -474,20 +506,17 @@ int fa_b200_forward(const fa_b200_params* p) {
   // one CTA per work item; resident CTAs steal the not-yet-launched ones (cluster launch control), so the
   // kernel behaves as a persistent kernel with a dynamic hardware scheduler
   if (nsplit > 1) {
-    apply_split(a, nsplit, p->B);
-    a.lse = ws_lse;
-    a.m = ws_m;
-    a.l = nullptr;
-    a.stat_stride_h = Nq;
-    a.stat_stride_b = (long long)p->H * Nq;
+    apply_split(a, nsplit, split_begin);
+    a.ws_lse = ws_lse;
+    a.ws_m = ws_m;
   }
   const long long grid = a.num_items;
   const bool bf16 = p->dtype == FA_B200_BF16;
   const bool causal = p->causal != 0;
   const bool precise = p->precise != 0;
 #define FA_LAUNCH(D_, BF_, C_)                                                             \
-  rc = precise ? launch<D_, BF_, C_, true>(tq, tk, tv, to, a, grid, stream)                \
-               : launch<D_, BF_, C_, false>(tq, tk, tv, to, a, grid, stream)
+  rc = precise ? launch<D_, BF_, C_, true>(tq, tk, tv, to, tw, a, grid, stream)            \
+               : launch<D_, BF_, C_, false>(tq, tk, tv, to, tw, a, grid, stream)
   if (dk == 128) {
     if (bf16) { if (causal) FA_LAUNCH(128, true, true); else FA_LAUNCH(128, true, false); }
     else      { if (causal) FA_LAUNCH(128, false, true); else FA_LAUNCH(128, false, false); }
@@ -500,8 +529,8 @@ int fa_b200_forward(const fa_b200_params* p) {
   }
 #undef FA_LAUNCH
   if (rc || nsplit == 1) return rc;
-  return fa::launch_split_combine(ws_o, ws_lse, ws_m, p->O, p->lse, p->l, p->m, nsplit, rows_total, d, p->H, Nq, os.b, os.h,
-                                  os.n, ssb, ssh, p->dtype, stream);
+  return fa::launch_item_combine(ws_o, ws_lse, ws_m, p->O, p->lse, p->l, p->m, a, d, os.b, os.h, os.n, ssb, ssh, p->dtype, causal,
+                                 stream);
 }
 
 int fa_b200_forward_legacy(const void* Q, const void* K, const void* V, void* O, float* l, float* m,

@@ -44,16 +44,23 @@ struct FwdArgs {
   int num_items;    // B*H*num_q_blocks work items (= grid size; later ones are stolen by resident CTAs)
   int num_bh;       // B*H
   int group_heads;  // causal item ordering: heads per L2-sized group (see get_item)
-  // split-KV (launches with fewer items than SMs): every (b,h,q-block) is cut into `nsplit` items that each visit
-  // `tiles_per_split` consecutive K/V tiles and write a partial (O, lse, m) for batch index split*B + b of the
-  // workspace; fa_split_combine_kernel merges them.  nsplit == 1: off.
-  int nsplit, tiles_per_split, B;
+  // split-KV: the (b,h,q-block) items from list position `split_begin` on are each cut into `nsplit` items that visit
+  // `tiles_per_split` consecutive K/V tiles and write a partial (O, lse, m) into the caller's workspace, laid out by item:
+  // [nsplit][num_ws_items][256 rows][d] / [nsplit][num_ws_items][256]; fa::item_combine_kernel merges them.
+  //   split_begin == 0: launches with far fewer items than SMs (every item is split);
+  //   split_begin  > 0: "tail split" - a launch whose last, partly filled wave of equal items would cost a whole round
+  //                     (512 items on 148 SMs = 3.46 waves) gets only that tail cut, so the tail takes 1/nsplit of a round.
+  // nsplit == 1: off.
+  int nsplit, tiles_per_split, split_begin, num_ws_items;
+  float* ws_lse;    // [nsplit][num_ws_items][256]
+  float* ws_m;
   float scale_log2; // softmax_scale * log2(e)
+  int need_stats;   // the caller wants l / m (reference semantics): every tile takes the exact-row-max path
   long long stat_stride_b, stat_stride_h;
   int H;            // heads per batch (a work item's bh is split into (b, h) for the 4-D tensor maps)
   // Order of the three outer tensor-map axes for Q, K/V and O: axis k of the map carries the row (0), head (1) or
   // batch (2) coordinate, 2 bits each (the host sorts the axes by stride, see make_tmap).
-  unsigned int perm_q, perm_kv, perm_o;
+  unsigned int perm_q, perm_kv, perm_o, perm_w;
   unsigned long long desc_hi_qk;  // K-major 128B-swizzle descriptor bits (Q, K)
   unsigned long long desc_hi_v;   // MN-major 128B-swizzle descriptor bits (V)
   unsigned int idesc_qk, idesc_pv;
@@ -74,6 +81,13 @@ constexpr int kBlockN = 128;        // keys per K/V tile
 constexpr int kNumThreads = 512;
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum on sm_100
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+// Fast softmax path (no row-max pass): a tile keeps the reference max it inherited as long as the sum of the
+// exponentials of each published part stays below this bound (so every p < 2^15: finite in fp16, harmless in bf16 and
+// in the fp32 sums); otherwise the tile is redone on the exact path.  0 compiles the fast path out (A/B switch).
+constexpr float kFastSumLimit = 32768.0f;
+#ifndef FA_FAST_SOFTMAX
+#define FA_FAST_SOFTMAX 0
+#endif
 
 template <int D>
 struct FwdTraits {
@@ -174,19 +188,15 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, uint32_t s
 struct WorkItem {
   int bh, q0, n_t0, n_t1, n_max;
   int kv_begin;          // first K/V tile this item visits (non-zero only with split-KV)
-  int out_b;             // batch index used for the outputs (split * B + b with split-KV, else b)
+  int out_b;             // batch index of the outputs
+  int ws_item, split;    // split items: position in the workspace, split index
+  bool split_out;        // outputs go to the workspace (a partial), not to the caller's O / lse / l / m
   bool valid0, valid1;   // tile has at least one real query row
 };
 
+// (b*H+h, q-block) of the un-split list position w.
 template <bool kCausal>
-__host__ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
-  WorkItem it;
-  int qb;
-  int split = 0;
-  if (a.nsplit > 1) {       // split index is the fastest-varying part of the item id
-    split = w % a.nsplit;
-    w /= a.nsplit;
-  }
+__host__ __device__ __forceinline__ void item_coords(const FwdArgs& a, int w, int& bh, int& qb) {
   if (kCausal) {
     // Causal items differ in length (q-block qb visits qb+1.. K/V tiles), so the list is ordered
     // longest-first, but only within groups of `group_heads` heads whose K/V fit the L2 together:
@@ -197,12 +207,29 @@ __host__ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
     const int r = w - g * per_group;
     const int heads = (a.group_heads < a.num_bh - g * a.group_heads) ? a.group_heads : (a.num_bh - g * a.group_heads);
     const int qi = r / heads;
-    it.bh = g * a.group_heads + (r - qi * heads);
+    bh = g * a.group_heads + (r - qi * heads);
     qb = a.num_q_blocks - 1 - qi;
   } else {
-    it.bh = w / a.num_q_blocks;
-    qb = w - it.bh * a.num_q_blocks;
+    bh = w / a.num_q_blocks;
+    qb = w - bh * a.num_q_blocks;
   }
+}
+
+template <bool kCausal>
+__host__ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
+  WorkItem it;
+  int qb;
+  it.split = 0;
+  it.ws_item = 0;
+  it.split_out = false;
+  if (a.nsplit > 1 && w >= a.split_begin) {   // split index is the fastest-varying part of the item id
+    const int u = w - a.split_begin;
+    it.split = u % a.nsplit;
+    it.ws_item = u / a.nsplit;
+    it.split_out = true;
+    w = a.split_begin + it.ws_item;
+  }
+  item_coords<kCausal>(a, w, it.bh, qb);
   it.q0 = qb * 2 * kBlockM;
   const int n_kv_tiles = (a.Nkv + kBlockN - 1) / kBlockN;
   // number of K/V tiles each Q tile visits (masked tiles above the diagonal are skipped)
@@ -220,15 +247,14 @@ __host__ __device__ __forceinline__ WorkItem get_item(const FwdArgs& a, int w) {
   it.n_t1 = tiles_for(it.q0 + kBlockM);
   it.kv_begin = 0;
   it.out_b = it.bh / a.H;
-  if (a.nsplit > 1) {       // restrict both tiles to this split's K/V tile range
-    it.kv_begin = split * a.tiles_per_split;
+  if (it.split_out) {       // restrict both tiles to this split's K/V tile range
+    it.kv_begin = it.split * a.tiles_per_split;
     auto clampn = [&](int n) {
       n -= it.kv_begin;
       return n < 0 ? 0 : (n < a.tiles_per_split ? n : a.tiles_per_split);
     };
     it.n_t0 = clampn(it.n_t0);
     it.n_t1 = clampn(it.n_t1);
-    it.out_b += split * a.B;
   }
   it.n_max = it.n_t0 > it.n_t1 ? it.n_t0 : it.n_t1;
   it.valid0 = it.q0 < a.Nq;
@@ -247,7 +273,7 @@ template <int D, bool kBF16, bool kCausal, bool kPrecise = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                    const FwdArgs a) {
+                    const __grid_constant__ CUtensorMap tmW, const FwdArgs a) {
   using T = FwdTraits<D>;
   constexpr int kStages = T::kStages;
   constexpr uint32_t kTileBytes = T::kTileBytes;
@@ -275,6 +301,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t bar_kv_full = bars + 144;                 // [kStages]
   const uint32_t bar_kv_empty = bars + 144 + 8 * kStages;  // [kStages]
   const uint32_t tmem_slot = bars + 144 + 16 * kStages;    // u32 written by tcgen05.alloc
+  const uint32_t bar_pv_part = bars + 384;                 // [2]  MMA -> softmax (first part of a PV has landed)
   const uint32_t bar_clc_full = bars + 416;                // [2]  CLC response landed (16 tx bytes)
   const uint32_t bar_clc_empty = bars + 432;               // [2]  all 14 consumer warps have read the response
   const uint32_t clc_resp = bars + 448;                    // [2] x 16 B
@@ -302,6 +329,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     prefetch_tensormap(&tmK);
     prefetch_tensormap(&tmV);
     prefetch_tensormap(&tmO);
+    if (a.nsplit > 1) prefetch_tensormap(&tmW);
   }
   if (warp == 13 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -309,6 +337,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(bar_q_empty + 8 * i, 1);
       mbar_init(bar_s_full + 8 * i, 1);
       mbar_init(bar_o_full + 8 * i, 1);
+      mbar_init(bar_pv_part + 8 * i, 1);
       mbar_init(bar_o_free + 8 * i, 128);
       mbar_init(bar_ep_full + 8 * i, 128);
       mbar_init(bar_ep_empty + 8 * i, 128);
@@ -437,7 +466,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               for (int k = (h ? 2 * FA_P_FIRST_Q : 0); k < (h ? 8 : 2 * FA_P_FIRST_Q); ++k)
                 umma_ts(d_tmem, p_tmem + kBlockN / 2 + k * 8, b_lo + k * (16 * kRowBytes / 16), hi_v, idesc_pv, 1u);
             }
-            if (h == 1) {
+            if (h == 0) {
+              umma_commit(bar_pv_part + 8 * i);   // only waited for by the softmax warps' rare mid-tile rescale
+            } else {
               umma_commit(bar_done);
               if (bar_release) umma_commit(bar_release);
             }
@@ -579,8 +610,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         named_bar_sync(2, 128);
         if (row_in_tile == 0) {
 #pragma unroll
-          for (int h = 0; h < kNumBoxes; ++h)
-            tma_store_tile(&tmO, sO + h * kBoxBytes, h * kBoxCols, wi.q0 + i * kBlockM, wi.bh % a.H, wi.out_b, a.perm_o);
+          for (int h = 0; h < kNumBoxes; ++h) {
+            if (wi.split_out)     // a partial: workspace tile (split, item, rows i*128..) instead of the caller's O
+              tma_store_tile(&tmW, sO + h * kBoxBytes, h * kBoxCols, i * kBlockM, wi.ws_item, wi.split, a.perm_w);
+            else
+              tma_store_tile(&tmO, sO + h * kBoxBytes, h * kBoxCols, wi.q0 + i * kBlockM, wi.bh % a.H, wi.out_b, a.perm_o);
+          }
           tma_store_commit();
         }
         store_pending = true;
@@ -637,60 +672,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_wait_ld();
         if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 1);
 
-        // masking: key index > limit -> -inf (diagonal tiles of causal runs, ragged last tile)
-        const int lim_local = limit - (kv_begin + j) * kBlockN;
-        if (__any_sync(0xffffffffu, lim_local < kBlockN - 1)) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (q * 32 + k > lim_local) sr[q][k] = 0xff800000u;  // -inf
-        }
-
-        // row max with four independent chains (a single chain of 64 dependent FMNMX3 costs ~4 clk each)
-        float mxp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int k = 0; k < 32; k += 8)
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              mxp[u] = fmaxf(mxp[u], fmaxf(__uint_as_float(sr[q][k + 2 * u]), __uint_as_float(sr[q][k + 2 * u + 1])));
-        const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
-        const float m_new = fmaxf(m_true, mx * c);
-        m_true = m_new;
-        if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 14 + i);
-
-        if (j == 0) {
-          m_ref = m_new;
-        } else {
-          const bool moved = (m_new - m_ref) > kRescaleThreshold;
-          if (__any_sync(0xffffffffu, moved)) {
-            // rescale this warp's 32 rows of O (and l) to the new reference max
-            const float alpha = (m_new == -INFINITY) ? 1.f : ex2_approx(m_ref - m_new);
-            m_ref = m_new;
-            l *= alpha;
-            mbar_wait(b_o_full, par ^ 1u, 310 + i);  // PV(j-1) has landed in TMEM
-            tc_fence_after();
-#pragma unroll
-            for (int q = 0; q < D / 32; ++q) {
-              uint32_t orow[32];
-              tmem_ld32(tO + q * 32, orow);
-              tmem_wait_ld();
-#pragma unroll
-              for (int k = 0; k < 32; ++k) orow[k] = __float_as_uint(__uint_as_float(orow[k]) * alpha);
-              tmem_st32(tO + q * 32, orow);
-            }
-          }
-        }
-        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-
-        // p = 2^(s*c - m_ref) with packed (2-wide) fp32 math; FA_EMU_PAIRS_OF_4 of every 4 pairs take the
-        // polynomial path, the rest MUFU.EX2.  P is published to the MMA warp in two halves of 64 keys.
-        const float2 c2 = make_float2(c, c), neg_m2 = make_float2(neg_m, neg_m);
-        float2 lsum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        const float2 c2 = make_float2(c, c);
+        // p = 2^(s*c + neg_m) for the 32 keys of group q, with packed (2-wide) fp32 math; FA_EMU_PAIRS_OF_4 of every 4
+        // pairs take the polynomial path, the rest MUFU.EX2.  P (16-bit) goes over the first 64 columns of S.
+        auto exp_group = [&](int q, const float2 neg_m2, float2 (&lsum2)[4]) {
           uint32_t pk[16];
           [[maybe_unused]] uint32_t pl[16];
 #pragma unroll
@@ -711,17 +696,126 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               pl[k] = pack2<kBF16>(__fadd2_rn(pv, make_float2(-hi.x, -hi.y)));
             }
           }
-          tmem_st16(tS + q * 16, pk);   // P(16-bit) over the first 64 columns of S
+          tmem_st16(tS + q * 16, pk);
           if constexpr (kPrecise) tmem_st16(tS + kBlockN / 2 + q * 16, pl);   // P_lo over columns 64..127
-          if (q == FA_P_FIRST_Q - 1 || q == 3) {
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(b_p_full + 8 * (q == 3 ? 1 : 0));
-            if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 2 + (q == 3 ? 1 : 0));
+        };
+        auto publish = [&](int part) {   // P columns written so far are visible to the MMA warp
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(b_p_full + 8 * part);
+          if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 2 + part);
+        };
+        auto total = [](const float2 (&v)[4]) {
+          const float2 r = __fadd2_rn(__fadd2_rn(v[0], v[1]), __fadd2_rn(v[2], v[3]));
+          return r.x + r.y;
+        };
+        // O_i (this warp's 32 rows) *= alpha, in TMEM
+        auto rescale_o = [&](float alpha) {
+#pragma unroll
+          for (int q = 0; q < D / 32; ++q) {
+            uint32_t orow[32];
+            tmem_ld32(tO + q * 32, orow);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) orow[k] = __float_as_uint(__uint_as_float(orow[k]) * alpha);
+            tmem_st32(tO + q * 32, orow);
+          }
+        };
+        auto group_max = [&](int q0, int q1) {   // four independent chains (a chain of dependent FMNMX3 costs ~4 clk each)
+          float mxp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int q = q0; q < q1; ++q)
+#pragma unroll
+            for (int k = 0; k < 32; k += 8)
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                mxp[u] = fmaxf(mxp[u], fmaxf(__uint_as_float(sr[q][k + 2 * u]), __uint_as_float(sr[q][k + 2 * u + 1])));
+          return fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+        };
+
+        // masking: key index > limit -> -inf (diagonal tiles of causal runs, ragged last tile)
+        const int lim_local = limit - (kv_begin + j) * kBlockN;
+        const bool masked = __any_sync(0xffffffffu, lim_local < kBlockN - 1);
+
+        // ---- fast path: no row-max pass.  The tile is exponentiated against the reference max it inherited; the
+        // sum of each published part bounds every p of that part (p <= sum <= 2^15), so a part is only handed to the
+        // MMA warp when it is known to be finite and harmless.  A first part that fails sends the whole tile to the
+        // exact path below (S is still in registers, nothing was published); a second part that fails waits for the
+        // first part's PV MMAs, rescales O and l to the new max and is exponentiated again.
+        bool done = false;
+        if (FA_FAST_SOFTMAX && !kPrecise && j > 0 && !masked && !a.need_stats) {
+          const float neg_m = -m_ref;     // finite: the row saw a whole unmasked tile before
+          float2 neg_m2 = make_float2(neg_m, neg_m);
+          float2 ls0[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+          for (int q = 0; q < FA_P_FIRST_Q; ++q) exp_group(q, neg_m2, ls0);
+          const float sum0 = total(ls0);
+          if (!__any_sync(0xffffffffu, !(sum0 <= kFastSumLimit))) {
+            publish(0);
+            float2 ls1[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+            for (int q = FA_P_FIRST_Q; q < 4; ++q) exp_group(q, neg_m2, ls1);
+            float sum1 = total(ls1);
+            l += sum0;
+            if (__any_sync(0xffffffffu, !(sum1 <= kFastSumLimit))) {
+              const float m_new = fmaxf(m_ref, group_max(FA_P_FIRST_Q, 4) * c);
+              m_true = fmaxf(m_true, m_new);
+              const float alpha = ex2_approx(m_ref - m_new);
+              m_ref = m_new;
+              l *= alpha;
+              mbar_wait(bar_pv_part + 8 * i, par, 320 + i);   // the first part's MMAs have landed in O_i
+              tc_fence_after();
+              rescale_o(alpha);
+              neg_m2 = make_float2(-m_ref, -m_ref);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) ls1[u] = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int q = FA_P_FIRST_Q; q < 4; ++q) exp_group(q, neg_m2, ls1);
+              sum1 = total(ls1);
+            }
+            publish(1);
+            l += sum1;
+            done = true;
           }
         }
-        const float2 lsum = __fadd2_rn(__fadd2_rn(lsum2[0], lsum2[1]), __fadd2_rn(lsum2[2], lsum2[3]));
-        l += lsum.x + lsum.y;
+
+        if (!done) {
+          // ---- exact path: mask, row max, lazy rescale, exponentials
+          if (masked) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (q * 32 + k > lim_local) sr[q][k] = 0xff800000u;  // -inf
+          }
+          const float m_new = fmaxf(m_true, group_max(0, 4) * c);
+          m_true = m_new;
+          if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 14 + i);
+
+          if (j == 0) {
+            m_ref = m_new;
+          } else {
+            const bool moved = (m_new - m_ref) > kRescaleThreshold;
+            if (__any_sync(0xffffffffu, moved)) {
+              // rescale this warp's 32 rows of O (and l) to the new reference max
+              const float alpha = (m_new == -INFINITY) ? 1.f : ex2_approx(m_ref - m_new);
+              m_ref = m_new;
+              l *= alpha;
+              mbar_wait(b_o_full, par ^ 1u, 310 + i);  // PV(j-1) has landed in TMEM
+              tc_fence_after();
+              rescale_o(alpha);
+            }
+          }
+          const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+          const float2 neg_m2 = make_float2(neg_m, neg_m);
+          float2 lsum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            exp_group(q, neg_m2, lsum2);
+            if (q == FA_P_FIRST_Q - 1 || q == 3) publish(q == 3 ? 1 : 0);
+          }
+          l += total(lsum2);
+        }
       }
       cnt += uint32_t(n_i);
 
@@ -735,12 +829,18 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const WorkItem wi = get_item<kCausal>(a, w_cur);   // recomputed here to keep it out of the hot loop's registers
       const int row = wi.q0 + i * kBlockM + row_in_tile;
       if (row < a.Nq) {
-        const long long off = (long long)wi.out_b * a.stat_stride_b + (long long)(wi.bh % a.H) * a.stat_stride_h + row;
         const float ln2 = 0.6931471805599453f;
         const bool any = l > 0.f;
-        if (a.lse) a.lse[off] = any ? fmaf(m_ref, ln2, logf(l)) : -INFINITY;
-        if (a.m) a.m[off] = any ? m_true * ln2 : -INFINITY;
-        if (a.l) a.l[off] = any ? l * ex2_approx(m_ref - m_true) : 0.f;
+        if (wi.split_out) {
+          const long long off = ((long long)wi.split * a.num_ws_items + wi.ws_item) * (2 * kBlockM) + i * kBlockM + row_in_tile;
+          a.ws_lse[off] = any ? fmaf(m_ref, ln2, logf(l)) : -INFINITY;
+          a.ws_m[off] = any ? m_true * ln2 : -INFINITY;
+        } else {
+          const long long off = (long long)wi.out_b * a.stat_stride_b + (long long)(wi.bh % a.H) * a.stat_stride_h + row;
+          if (a.lse) a.lse[off] = any ? fmaf(m_ref, ln2, logf(l)) : -INFINITY;
+          if (a.m) a.m[off] = any ? m_true * ln2 : -INFINITY;
+          if (a.l) a.l[off] = any ? l * ex2_approx(m_ref - m_true) : 0.f;
+        }
       }
     }
   }

@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/fa_b200.h"
+#include "fa_fwd_sm100.cuh"
 
 namespace fa {
 void count_launch();
@@ -18,14 +19,6 @@ int api_fail(int code, const char* msg);
 int api_check_device();
 int api_sm_count();
 
-template <bool kBF16>
-__device__ __forceinline__ float2 unpack2(uint32_t u) {
-  if constexpr (kBF16) {
-    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
-  } else {
-    return __half22float2(*reinterpret_cast<__half2*>(&u));
-  }
-}
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2f(float a, float b) {
   if constexpr (kBF16) {
@@ -150,6 +143,65 @@ split_combine_kernel(const uint4* __restrict__ O_part, const float* __restrict__
   }
 }
 
+// Combine of the forward kernel's split items (FwdArgs::nsplit > 1): partials are laid out by item,
+// O_part [nsplit][num_ws_items][256][d], lse_part / m_part [nsplit][num_ws_items][256]; item t of the workspace is list
+// position split_begin + t, i.e. rows q0 .. q0+255 of slice bh (item_coords).  Same arithmetic as split_combine_kernel;
+// the outputs use the caller's strides.  One thread per 8 consecutive elements of a row.
+template <bool kBF16, bool kCausal>
+__global__ void __launch_bounds__(256)
+item_combine_kernel(const uint4* __restrict__ O_part, const float* __restrict__ lse_part, const float* __restrict__ m_part,
+                    char* __restrict__ O, float* __restrict__ lse, float* __restrict__ l, float* __restrict__ m,
+                    const FwdArgs a, int d, long long o_sb, long long o_sh, long long o_sn, long long st_sb, long long st_sh) {
+  const int vec_per_row = d / 8;
+  const int rows_per_item = 2 * kBlockM;
+  const long long part_rows = (long long)a.num_ws_items * rows_per_item;
+  const long long total = part_rows * vec_per_row;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long prow = idx / vec_per_row;              // row inside one split's partial
+    const int v = (int)(idx - prow * vec_per_row);
+    const int t = (int)(prow / rows_per_item), r = (int)(prow - (long long)t * rows_per_item);
+    int bh, qb;
+    item_coords<kCausal>(a, a.split_begin + t, bh, qb);
+    const int n = qb * rows_per_item + r;
+    if (n >= a.Nq) continue;
+    float mx = -INFINITY;
+    for (int s = 0; s < a.nsplit; ++s) mx = fmaxf(mx, lse_part[s * part_rows + prow]);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float sum = 0.f;
+    if (mx != -INFINITY) {
+      for (int s = 0; s < a.nsplit; ++s) {
+        const float ls = lse_part[s * part_rows + prow];
+        if (ls == -INFINITY) continue;
+        const float w = __expf(ls - mx);
+        sum += w;
+        const uint4 pv = O_part[(s * part_rows + prow) * vec_per_row + v];
+        const float2 p0 = unpack2<kBF16>(pv.x), p1 = unpack2<kBF16>(pv.y), p2 = unpack2<kBF16>(pv.z),
+                     p3 = unpack2<kBF16>(pv.w);
+        acc[0] += w * p0.x; acc[1] += w * p0.y; acc[2] += w * p1.x; acc[3] += w * p1.y;
+        acc[4] += w * p2.x; acc[5] += w * p2.y; acc[6] += w * p3.x; acc[7] += w * p3.y;
+      }
+    }
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    const long long b = bh / a.H, h = bh - b * a.H;
+    uint4 o;
+    o.x = pack2f<kBF16>(acc[0] * inv, acc[1] * inv); o.y = pack2f<kBF16>(acc[2] * inv, acc[3] * inv);
+    o.z = pack2f<kBF16>(acc[4] * inv, acc[5] * inv); o.w = pack2f<kBF16>(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(O + (b * o_sb + h * o_sh + n * o_sn + v * 8) * 2) = o;
+    if (v == 0) {
+      const long long so = b * st_sb + h * st_sh + n;
+      const float lse_v = sum > 0.f ? mx + __logf(sum) : -INFINITY;
+      if (lse) lse[so] = lse_v;
+      if (m || l) {
+        float mm = -INFINITY;
+        for (int s = 0; s < a.nsplit; ++s) mm = fmaxf(mm, m_part[s * part_rows + prow]);
+        if (m) m[so] = mm;
+        if (l) l[so] = sum > 0.f ? __expf(lse_v - mm) : 0.f;
+      }
+    }
+  }
+}
+
 // 32-bit pattern fill (the ring driver's "lse = -inf" reset of its partial stack)
 __global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* __restrict__ dst, uint32_t value, long long count) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
@@ -185,6 +237,23 @@ int launch_split_combine(const void* O_part, const float* lse_part, const float*
   count_launch();
   return FA_B200_OK;
 }
+int launch_item_combine(const void* O_part, const float* lse_part, const float* m_part, void* O, float* lse, float* l, float* m,
+                        const FwdArgs& a, int d, long long o_sb, long long o_sh, long long o_sn, long long st_sb, long long st_sh,
+                        int dtype, bool causal, cudaStream_t stream) {
+  const long long total = (long long)a.num_ws_items * 2 * kBlockM * (d / 8);
+  const unsigned grid = grid_for(total);
+#define FA_IC(BF_, C_)                                                                                                   \
+  item_combine_kernel<BF_, C_><<<grid, 256, 0, stream>>>((const uint4*)O_part, lse_part, m_part, (char*)O, lse, l, m, a, d, o_sb, \
+                                                         o_sh, o_sn, st_sb, st_sh)
+  if (dtype == FA_B200_BF16) { if (causal) FA_IC(true, true); else FA_IC(true, false); }
+  else                       { if (causal) FA_IC(false, true); else FA_IC(false, false); }
+#undef FA_IC
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_fail(FA_B200_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return FA_B200_OK;
+}
+
 int launch_fill_u32(uint32_t* dst, uint32_t value, long long count, cudaStream_t stream) {
   fill_u32_kernel<<<grid_for(count), 256, 0, stream>>>(dst, value, count);
   cudaError_t e = cudaGetLastError();

@@ -160,7 +160,10 @@ def test_workspace_query_policy():
     """Split-KV is only proposed for launches that would leave most SMs idle and are long enough to cut."""
     lib = _lib.load()
     assert lib.fa_b200_workspace_bytes(4, 32, 8192, 0, 128) == 0          # c3: 4096 items, no split
-    assert lib.fa_b200_workspace_bytes(8, 16, 1024, 0, 64) == 0           # c2: 512 items
+    assert lib.fa_b200_workspace_bytes(8, 16, 1024, 0, 64) == 0           # c2: 512 items of 8 K/V tiles: too short for a tail split
+    # c3 sharded over 8 GPUs: 512 equal items on 148 SMs = 3.46 waves: the 68 items of the last wave are split in two
+    assert lib.fa_b200_workspace_bytes(1, 16, 8192, 0, 128) == 2 * 68 * 256 * (128 * 2 + 8)
+    assert lib.fa_b200_workspace_bytes(1, 37, 1024, 0, 64) == 0           # 148 items: exactly one wave
     assert lib.fa_b200_workspace_bytes(1, 1, 512, 0, 64) == 0             # too short to split
     n = lib.fa_b200_workspace_bytes(1, 1, 8192, 0, 64)                    # the reference's (1,1,8192,64) sweep point
     assert n > 0 and n % (8192 * (64 * 2 + 8)) == 0

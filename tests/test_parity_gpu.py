@@ -33,17 +33,32 @@ def _dt(name):
 
 
 def _run(fa, q, k, v, dtype, causal, stats=True):
+    """Runs the forward twice when `stats` is set: once asking for l / m (the kernel then takes its exact-row-max path on
+    every tile) and once without (fast path: tiles inherit the reference max and are only checked for overflow).  Returns
+    the fast-path O / lse (the product default, checked against the oracle by the caller) and the exact path's l / m; the
+    two O / lse pairs must agree to rounding."""
     dev = torch.device("cuda:0")
     tq, tk, tv = (torch.from_numpy(x).to(dev, dtype) for x in (q, k, v))
     B, H, N, _ = q.shape
-    l = torch.empty((B, H, N), dtype=torch.float32, device=dev) if stats else None
-    m = torch.empty_like(l) if stats else None
     before = fa.launch_count()
-    o, lse = fa.attention_forward(tq, tk, tv, causal=causal, l=l, m=m)
+    o, lse = fa.attention_forward(tq, tk, tv, causal=causal)
     torch.cuda.synchronize()
     # the CUDA kernel really launched (+1 combine kernel when the split-KV schedule was picked)
     assert fa.launch_count() - before in (1, 2)
-    return o.float().cpu().numpy(), lse.cpu().numpy(), (l.cpu().numpy() if stats else None), (m.cpu().numpy() if stats else None)
+    o, lse = o.float().cpu().numpy(), lse.cpu().numpy()
+    if not stats:
+        return o, lse, None, None
+    l = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+    m = torch.empty_like(l)
+    o_x, lse_x = fa.attention_forward(tq, tk, tv, causal=causal, l=l, m=m)
+    torch.cuda.synchronize()
+    o_x, lse_x = o_x.float().cpu().numpy(), lse_x.cpu().numpy()
+    fin = np.isfinite(lse_x)
+    assert np.array_equal(np.isfinite(lse), fin)
+    assert np.abs(o - o_x).max() <= O_TOL
+    if fin.any():
+        assert (np.abs(lse[fin] - lse_x[fin]) / np.maximum(1.0, np.abs(lse_x[fin]))).max() <= 2e-6
+    return o, lse, l.cpu().numpy(), m.cpu().numpy()
 
 
 def _check(o, lse, o_ref, lse_ref):
@@ -159,7 +174,9 @@ def test_precise_p_mode_matches_oracle_and_is_no_less_accurate(fa, B, H, N, Nkv,
     o1, lse1 = fa.attention_forward(tq, tk, tv, causal=causal, precise=True)
     torch.cuda.synchronize()
     _check(o1.float().cpu().numpy(), lse1.cpu().numpy(), o_ref, lse_ref)
-    assert torch.equal(lse0, lse1)            # the statistics do not depend on how P is fed to the tensor cores
+    # the statistics do not depend on how P is fed to the tensor cores (up to the rounding of lse = m_ref ln2 + ln l,
+    # whose reference max differs between the fast and the exact softmax path)
+    assert (lse0 - lse1).abs().max().item() <= 2e-5
     e0 = np.abs(o0.float().cpu().numpy() - o_ref).mean()
     e1 = np.abs(o1.float().cpu().numpy() - o_ref).mean()
     assert e1 <= e0 * 1.02 + 1e-9
@@ -598,3 +615,68 @@ def test_broadcast_and_odd_stride_views_are_copied_not_misread(fa):
     # an output the descriptors cannot address is an error, not a silent copy
     with pytest.raises(ValueError):
         fa.attention_forward(tq, ke, ve, out=torch.empty((B, 1, N, d), dtype=torch.bfloat16, device=dev).expand(B, H, N, d))
+
+
+@pytest.mark.parametrize("B,H,N,Nkv,d,dtype,causal,bnhd", [
+    (1, 19, 2048, 3072, 128, "bf16", False, False),    # 152 items on 148 SMs: the 4 tail items are split 6 ways
+    (1, 19, 2000, 3100, 128, "fp16", False, True),     # ragged last q-block inside the split tail, [B,N,H,d] output
+    (2, 13, 2304, 3072, 64, "bf16", False, False),     # 234 items: 86 > 74 in the last wave -> no tail split (control)
+    (1, 19, 2048, 2048, 128, "bf16", False, False),    # 152 items of 16 K/V tiles: too short -> control
+    (3, 10, 1280, 3100, 32, "bf16", False, False),     # 150 items: tail 2, ragged keys, d = 32
+])
+def test_tail_split_of_the_last_partial_wave(fa, B, H, N, Nkv, d, dtype, causal, bnhd):
+    """Non-causal launches of equal items whose last wave fills at most half of the SMs get only that tail cut along
+    the key axis (fa_api.cu::choose_nsplit, split_begin > 0): whole items write O / lse / l / m directly, tail items
+    write item-indexed partials that item_combine_kernel merges.  Every output against the oracle, all rows."""
+    from oracle import oracle
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, Nkv, d), seeds=(111, 112, 113))
+    dev = torch.device("cuda:0")
+    dt = _dt(dtype)
+    tq, tk, tv = (torch.from_numpy(x).to(dev, dt) for x in (q, k, v))
+    l = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+    m = torch.empty_like(l)
+    out = torch.empty((B, N, H, d), dtype=dt, device=dev).transpose(1, 2) if bnhd else None
+    ws = fa.load().fa_b200_workspace_bytes(B, H, N, 0 if Nkv == N else Nkv, d)
+    before = fa.launch_count()
+    o, lse = fa.attention_forward(tq, tk, tv, causal=causal, out=out, l=l, m=m)
+    torch.cuda.synchronize()
+    assert fa.launch_count() - before == (2 if ws else 1)
+    o_ref, lse_ref, l_ref, m_ref = oracle.attention(q, k, v, causal=causal)
+    _check(o.float().cpu().numpy(), lse.cpu().numpy(), o_ref, lse_ref)
+    assert np.abs(m.cpu().numpy() - m_ref).max() <= 1e-3
+    assert (np.abs(l.cpu().numpy() - l_ref) / l_ref).max() <= 1e-3
+    # and identical (up to the merge's rounding) to the unsplit schedule
+    o1, lse1 = fa.attention_forward(tq, tk, tv, causal=causal, allow_split=False)
+    assert (o.float() - o1.float()).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("spikes", [
+    [(3 * 128 + 100, 1.0)],                                   # second published part of tile 3: mid-tile rescale
+    [(2 * 128 + 10, 1.0)],                                    # first part of tile 2: whole tile redone on the exact path
+    [(1 * 128 + 70, 0.4), (2 * 128 + 5, 0.7), (5 * 128 + 127, 1.0), (6 * 128 + 64, 1.3)],   # several, growing
+    [(k * 128 + 64 + k, 0.2 * (k + 1)) for k in range(1, 8)],  # every tile overflows in its second part
+])
+def test_fast_softmax_path_overflow_handling(fa, dtype, spikes):
+    """The fast softmax path (no l / m requested) exponentiates a tile against the reference max it inherited and hands
+    a part of P to the tensor cores only when the part's row sum proves every p < 2^15; keys whose scores tower 2^20 and
+    more above everything before them must send the tile to the exact path (first part) or through the mid-tile rescale
+    (second part) - in fp16 a missed one is an inf in O.  Half of the rows have q > 0 (they see the spike), the others
+    q < 0 (for them the same key underflows), so both branches run inside one warp vote."""
+    from oracle import oracle
+    B, H, N, d = 1, 3, 1024, 128
+    q, k, v = oracle.set_s((B, H, N, d), (B, H, N, d), seeds=(201, 202, 203))
+    q = np.abs(q)
+    q[:, :, 1::2, :] *= -1.0
+    for pos, amp in spikes:
+        k[:, :, pos, :] = 3.0 * amp
+    dt = _dt(dtype)
+    q, k, v = (torch.from_numpy(x).to(dt).float().numpy() for x in (q, k, v))
+    o, lse, l, m = _run(fa, q, k, v, dt, False)
+    o_ref, lse_ref, l_ref, m_ref = oracle.attention(q, k, v)
+    _check(o, lse, o_ref, lse_ref)
+    assert np.abs(m - m_ref).max() <= 1e-3 * np.maximum(1.0, np.abs(m_ref)).max()
+    # causal too: the spike sits above the diagonal for the early rows
+    o, lse, _, _ = _run(fa, q, k, v, dt, True)
+    o_ref, lse_ref, _, _ = oracle.attention(q, k, v, causal=True)
+    _check(o, lse, o_ref, lse_ref)
