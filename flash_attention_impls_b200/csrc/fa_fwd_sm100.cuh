@@ -56,6 +56,7 @@ struct FwdArgs {
   float* ws_m;
   float scale_log2; // softmax_scale * log2(e)
   int need_stats;   // the caller wants l / m (reference semantics): every tile takes the exact-row-max path
+  unsigned int zero;   // always 0; opaque to the compiler (pins the position of an mbarrier arrival in the instruction stream)
   long long stat_stride_b, stat_stride_h;
   int H;            // heads per batch (a work item's bh is split into (b, h) for the 4-D tensor maps)
   // Order of the three outer tensor-map axes for Q, K/V and O: axis k of the map carries the row (0), head (1) or
@@ -81,12 +82,21 @@ constexpr int kBlockN = 128;        // keys per K/V tile
 constexpr int kNumThreads = 512;
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum on sm_100
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-// Fast softmax path (no row-max pass): a tile keeps the reference max it inherited as long as the sum of the
-// exponentials of each published part stays below this bound (so every p < 2^15: finite in fp16, harmless in bf16 and
-// in the fp32 sums); otherwise the tile is redone on the exact path.  0 compiles the fast path out (A/B switch).
+// Fast softmax path (no row-max pass; head dim 128 only): a tile keeps the reference max it inherited as long as the sum
+// of the exponentials of each published part stays below this bound (so every p < 2^15: finite in fp16, harmless in bf16
+// and in the fp32 sums); otherwise the tile is redone on the exact path.  0 compiles the fast path out (A/B switch).
+// Measured on zero inputs (SM clock at its maximum, i.e. in cycles): c3 1572 -> 1617 TFLOP/s, on Set S c3 best-of-20
+// 1391 -> 1413, c4 1284 -> 1296; at d = 64 the kernel is MUFU-bound and the path costs 3 %, so it is not compiled in there
+// (profiles/r02_fast_softmax_ab.log).
 constexpr float kFastSumLimit = 32768.0f;
+// Timing-only ablations (results are WRONG; zero-input runs only): which instruction class the period is sensitive to.
+//   1: no row-sum FADD2   2: no FFMA2 (scale / subtract)   4: MUFU.EX2 on every other pair only   8: no row-max pass
+//   16: no tcgen05.wait::st before P is published   32: no F2FP pack   64: QK^T with half the k-steps   128: PV likewise
+#ifndef FA_ABLATE
+#define FA_ABLATE 0
+#endif
 #ifndef FA_FAST_SOFTMAX
-#define FA_FAST_SOFTMAX 0
+#define FA_FAST_SOFTMAX 1
 #endif
 
 template <int D>
@@ -437,7 +447,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t d_tmem = tmem_base + i * kBlockN;
         if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
+          for (int k = 0; k < ((FA_ABLATE & 64) ? D / 32 : D / 16); ++k) {
             const uint32_t off = ((k / 4) * kBoxBytes + (k % 4) * 32) >> 4;
             umma_ss(d_tmem, a_lo + off, hi_qk, b_lo + off, hi_qk, idesc_qk, k > 0 ? 1u : 0u);
           }
@@ -459,7 +469,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_fence_after();
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k = (h ? 2 * FA_P_FIRST_Q : 0); k < (h ? 8 : 2 * FA_P_FIRST_Q); ++k)
+            for (int k = (h ? 2 * FA_P_FIRST_Q : 0); k < (h ? 8 : 2 * FA_P_FIRST_Q); k += ((FA_ABLATE & 128) ? 2 : 1))
               umma_ts(d_tmem, p_tmem + k * 8, b_lo + k * (16 * kRowBytes / 16), hi_v, idesc_pv, (acc || k > 0) ? 1u : 0u);
             if constexpr (kPrecise) {   // O += P_lo V_j: the rounding residual of P, 64 columns further up
 #pragma unroll
@@ -675,22 +685,25 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float2 c2 = make_float2(c, c);
         // p = 2^(s*c + neg_m) for the 32 keys of group q, with packed (2-wide) fp32 math; FA_EMU_PAIRS_OF_4 of every 4
         // pairs take the polynomial path, the rest MUFU.EX2.  P (16-bit) goes over the first 64 columns of S.
-        auto exp_group = [&](int q, const float2 neg_m2, float2 (&lsum2)[4]) {
+        auto exp_group = [&](int q, const float2 neg_m2, float2 (&lsum2)[4], const float2 neg_late2, int late_from = 16) {
           uint32_t pk[16];
           [[maybe_unused]] uint32_t pl[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[q][2 * k]), __uint_as_float(sr[q][2 * k + 1])),
-                                        c2, neg_m2);
+            float2 x = make_float2(__uint_as_float(sr[q][2 * k]), __uint_as_float(sr[q][2 * k + 1]));
+            if (!(FA_ABLATE & 2)) x = __ffma2_rn(x, c2, k < late_from ? neg_m2 : neg_late2);
             float2 pv;
             if ((k & 3) < FA_EMU_PAIRS_OF_4) {
               pv = ex2_emulated(x);
+            } else if ((FA_ABLATE & 4) && (k & 1)) {
+              pv = x;
             } else {
               pv.x = ex2_approx(x.x);
               pv.y = ex2_approx(x.y);
             }
-            lsum2[k & 3] = __fadd2_rn(lsum2[k & 3], pv);
-            pk[k] = pack2<kBF16>(pv);
+            if (!(FA_ABLATE & 1)) lsum2[k & 3] = __fadd2_rn(lsum2[k & 3], pv);
+            else if (k == 0) lsum2[0] = __fadd2_rn(lsum2[0], pv);
+            pk[k] = (FA_ABLATE & 32) ? (__float_as_uint(pv.x) ^ (__float_as_uint(pv.y) >> 16)) : pack2<kBF16>(pv);
             if constexpr (kPrecise) {
               const float2 hi = unpack2<kBF16>(pk[k]);
               pl[k] = pack2<kBF16>(__fadd2_rn(pv, make_float2(-hi.x, -hi.y)));
@@ -699,10 +712,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_st16(tS + q * 16, pk);
           if constexpr (kPrecise) tmem_st16(tS + kBlockN / 2 + q * 16, pl);   // P_lo over columns 64..127
         };
-        auto publish = [&](int part) {   // P columns written so far are visible to the MMA warp
-          tmem_wait_st();
+        auto publish = [&](int part, bool already) {   // P columns written so far are visible to the MMA warp
+          if (!(FA_ABLATE & 16)) tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(b_p_full + 8 * part);
+          if (!already) mbar_arrive(b_p_full + 8 * part);
           if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 2 + part);
         };
         auto total = [](const float2 (&v)[4]) {
@@ -737,44 +750,64 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int lim_local = limit - (kv_begin + j) * kBlockN;
         const bool masked = __any_sync(0xffffffffu, lim_local < kBlockN - 1);
 
-        // ---- fast path: no row-max pass.  The tile is exponentiated against the reference max it inherited; the
-        // sum of each published part bounds every p of that part (p <= sum <= 2^15), so a part is only handed to the
-        // MMA warp when it is known to be finite and harmless.  A first part that fails sends the whole tile to the
-        // exact path below (S is still in registers, nothing was published); a second part that fails waits for the
-        // first part's PV MMAs, rescales O and l to the new max and is exponentiated again.
+        // ---- fast path: no row-max pass, no branch in the common case.  The tile is exponentiated against the
+        // reference max it inherited, and each thread hands a part of P to the MMA warp only if the part's row sum proves
+        // every p of the part finite and harmless (p <= sum <= 2^15) - a predicated arrival, so the instruction stream
+        // stays straight.  Only when a row of the warp failed (one vote at the end of the tile) is anything redone:
+        //   * a row failed in the first part: no PV MMA of this tile can have started (its arrival is missing), so the
+        //     whole tile goes through the exact path below, which arrives for the threads that have not yet;
+        //   * rows failed in the second part only: wait for the first part's PV MMAs, rescale O and l to the new max,
+        //     exponentiate the second part again.
         bool done = false;
-        if (FA_FAST_SOFTMAX && !kPrecise && j > 0 && !masked && !a.need_stats) {
-          const float neg_m = -m_ref;     // finite: the row saw a whole unmasked tile before
-          float2 neg_m2 = make_float2(neg_m, neg_m);
+        bool arrived0 = false, arrived1 = false;   // this thread's arrivals on p_full[0 / 1] for this tile
+        if (FA_FAST_SOFTMAX && D == 128 && !kPrecise && j > 0 && !masked && !a.need_stats) {
+          float2 neg_m2 = make_float2(-m_ref, -m_ref);     // finite: the row saw a whole unmasked tile before
           float2 ls0[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          float2 ls1[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-          for (int q = 0; q < FA_P_FIRST_Q; ++q) exp_group(q, neg_m2, ls0);
+          for (int q = 0; q < FA_P_FIRST_Q; ++q) exp_group(q, neg_m2, ls0, neg_m2);
           const float sum0 = total(ls0);
-          if (!__any_sync(0xffffffffu, !(sum0 <= kFastSumLimit))) {
-            publish(0);
-            float2 ls1[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          arrived0 = sum0 <= kFastSumLimit;
+          tmem_wait_st();
+          tc_fence_before();
+          // The arrival has no consumer, so the compiler would let it sink below all of the second part's exponentials
+          // (and the first PV MMAs would start that much later).  Its token is folded, as an opaque +0.0, into the
+          // reference value all but the first four pairs of the second part use: those four pairs (64 clk of MUFU)
+          // cover the store wait, the rest has to follow the arrival.
+          const uint32_t tok = mbar_arrive_if_token(b_p_full, arrived0);
+          const float neg_late = -m_ref + __uint_as_float(tok & a.zero);
+          const float2 neg_late2 = make_float2(neg_late, neg_late);
+          if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 2);
 #pragma unroll
-            for (int q = FA_P_FIRST_Q; q < 4; ++q) exp_group(q, neg_m2, ls1);
-            float sum1 = total(ls1);
-            l += sum0;
-            if (__any_sync(0xffffffffu, !(sum1 <= kFastSumLimit))) {
-              const float m_new = fmaxf(m_ref, group_max(FA_P_FIRST_Q, 4) * c);
-              m_true = fmaxf(m_true, m_new);
-              const float alpha = ex2_approx(m_ref - m_new);
-              m_ref = m_new;
-              l *= alpha;
-              mbar_wait(bar_pv_part + 8 * i, par, 320 + i);   // the first part's MMAs have landed in O_i
-              tc_fence_after();
-              rescale_o(alpha);
-              neg_m2 = make_float2(-m_ref, -m_ref);
+          for (int q = FA_P_FIRST_Q; q < 4; ++q) exp_group(q, neg_m2, ls1, neg_late2, q == FA_P_FIRST_Q ? 4 : 0);
+          float sum1 = total(ls1);
+          arrived1 = arrived0 && (sum1 <= kFastSumLimit);
+          tmem_wait_st();
+          tc_fence_before();
+          if (arrived1) mbar_arrive(b_p_full + 8);
+          if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 3);
+          if (!__any_sync(0xffffffffu, !arrived1)) {
+            l += sum0 + sum1;
+            done = true;
+          } else if (!__any_sync(0xffffffffu, !arrived0)) {
+            // second part only
+            const float m_new = arrived1 ? m_ref : fmaxf(m_ref, group_max(FA_P_FIRST_Q, 4) * c);
+            m_true = fmaxf(m_true, m_new);
+            const float alpha = ex2_approx(m_ref - m_new);
+            m_ref = m_new;
+            l = (l + sum0) * alpha;
+            mbar_wait(bar_pv_part + 8 * i, par, 320 + i);   // the first part's MMAs have landed in O_i
+            tc_fence_after();
+            rescale_o(alpha);
+            neg_m2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) ls1[u] = make_float2(0.f, 0.f);
+            for (int u = 0; u < 4; ++u) ls1[u] = make_float2(0.f, 0.f);
 #pragma unroll
-              for (int q = FA_P_FIRST_Q; q < 4; ++q) exp_group(q, neg_m2, ls1);
-              sum1 = total(ls1);
-            }
-            publish(1);
-            l += sum1;
+            for (int q = FA_P_FIRST_Q; q < 4; ++q) exp_group(q, neg_m2, ls1, neg_m2);
+            l += total(ls1);
+            tmem_wait_st();
+            tc_fence_before();
+            if (!arrived1) mbar_arrive(b_p_full + 8);
             done = true;
           }
         }
@@ -788,7 +821,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               for (int k = 0; k < 32; ++k)
                 if (q * 32 + k > lim_local) sr[q][k] = 0xff800000u;  // -inf
           }
-          const float m_new = fmaxf(m_true, group_max(0, 4) * c);
+          const float m_new = (FA_ABLATE & 8) ? fmaxf(m_true, __uint_as_float(sr[0][0]) * c) : fmaxf(m_true, group_max(0, 4) * c);
           m_true = m_new;
           if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 14 + i);
 
@@ -811,8 +844,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           float2 lsum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            exp_group(q, neg_m2, lsum2);
-            if (q == FA_P_FIRST_Q - 1 || q == 3) publish(q == 3 ? 1 : 0);
+            exp_group(q, neg_m2, lsum2, neg_m2);
+            if (q == FA_P_FIRST_Q - 1) publish(0, arrived0);
+            if (q == 3) publish(1, arrived1);
           }
           l += total(lsum2);
         }

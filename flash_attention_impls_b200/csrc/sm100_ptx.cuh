@@ -32,6 +32,19 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrives if `pred`; returns the low word of the arrival token (0 when not arrived), a value the compiler cannot see
+// through: code that consumes it stays behind the arrival in the instruction stream.
+__device__ __forceinline__ uint32_t mbar_arrive_if_token(uint32_t bar, bool pred) {
+  uint32_t tok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 t;\n\t"
+      "setp.ne.u32 p, %2, 0;\n\t"
+      "mov.b64 t, 0;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 t, [%1];\n\t"
+      "cvt.u32.u64 %0, t;\n\t}\n"
+      : "=r"(tok) : "r"(bar), "r"((uint32_t)pred) : "memory");
+  return tok;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");

@@ -551,8 +551,12 @@ def test_full_size_c3_c4_properties(fa, causal):
     for P, r in ((8, 3), (2, 1)):
         b0, b1 = fa.bh_shard_range(B * H, P, r)
         qs, ks, vs = (t.view(1, B * H, N, d)[:, b0:b1] for t in (q, k, v))
-        os_, ls_ = fa.attention_forward(qs, ks, vs, causal=causal)
+        os_, ls_ = fa.attention_forward(qs, ks, vs, causal=causal, allow_split=False)
         assert torch.equal(os_, o.view(1, B * H, N, d)[:, b0:b1]) and torch.equal(ls_, lse.view(1, B * H, N)[:, b0:b1])
+        # the shard's default schedule may cut its last partial wave along the key axis (16 heads = 512 items = 3.46
+        # waves of 148 SMs): same result up to the combine's rounding
+        os2, ls2 = fa.attention_forward(qs, ks, vs, causal=causal)
+        assert (os2.float() - os_.float()).abs().max().item() <= 1e-3 and (ls2 - ls_).abs().max().item() <= 2e-5
     # (3) causal: the first query row sees only key 0 -> O[0] == V[0] exactly, lse == s_00
     if causal:
         assert torch.equal(o[:, :, 0], v[:, :, 0])
@@ -670,6 +674,9 @@ def test_fast_softmax_path_overflow_handling(fa, dtype, spikes):
     q[:, :, 1::2, :] *= -1.0
     for pos, amp in spikes:
         k[:, :, pos, :] = 3.0 * amp
+    # a softmax this close to one-hot does not average P's bf16 rounding (2^-9 relative) over the keys; |V| <= 0.25 keeps
+    # that term plus the output's half-ulp inside the 2e-3 gate (as in test_large_score_range_exercises_lazy_rescale)
+    v = v * 0.5
     dt = _dt(dtype)
     q, k, v = (torch.from_numpy(x).to(dt).float().numpy() for x in (q, k, v))
     o, lse, l, m = _run(fa, q, k, v, dt, False)

@@ -18,15 +18,37 @@ __device__ __forceinline__ unsigned pack(float2 v) {
 }
 
 // bit 0: FFMA2 (scale/subtract), bit 1: MUFU, bit 2: FADD2 (row sum), bit 3: F2FP (pack)
-template <int MIX>
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+
+// SPIN: threads >= 128 (one or more extra warps per SMSP) spin on an mbarrier, as the kernel's waiting warps do, until
+// the four measured warps are done.
+template <int MIX, bool SPIN>
 __global__ void __launch_bounds__(256, 1) k(float* out, const float* in, int iters, long long* cyc) {
+  __shared__ __align__(8) unsigned long long bar;
+  if (SPIN) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar)), "r"(128));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x >= 128) {
+      while (!try_wait(smem_addr(&bar), 0)) {}
+      return;
+    }
+  }
   float s[128];
 #pragma unroll
   for (int i = 0; i < 128; ++i) s[i] = in[(threadIdx.x * 128 + i) & 1023];
   float c = in[3], nm = in[5];
   float2 ls[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
   unsigned acc = 0;
-  __syncthreads();
+  if (!SPIN) __syncthreads();
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
     const float2 c2 = make_float2(c, c), nm2 = make_float2(nm, nm);
@@ -52,22 +74,24 @@ __global__ void __launch_bounds__(256, 1) k(float* out, const float* in, int ite
   }
   const long long t1 = clock64();
   if (threadIdx.x == 0) *cyc = t1 - t0;
+  if (SPIN) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar)) : "memory");
   float r = 0.f;
 #pragma unroll
   for (int u = 0; u < 4; ++u) r += ls[u].x + ls[u].y;
   out[blockIdx.x * blockDim.x + threadIdx.x] = r + __uint_as_float(acc);
 }
 
-template <int MIX>
+template <int MIX, bool SPIN = false>
 void run(const char* name, int warps_per_smsp, float* in) {
   float* out; long long* cyc; long long h;
   cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 8);
   const int iters = 400, threads = 128 * warps_per_smsp;
-  k<MIX><<<1, threads>>>(out, in, 10, cyc);
-  k<MIX><<<1, threads>>>(out, in, iters, cyc);
+  k<MIX, SPIN><<<1, threads>>>(out, in, 10, cyc);
+  k<MIX, SPIN><<<1, threads>>>(out, in, iters, cyc);
   cudaDeviceSynchronize();
   cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
   const double per_tile = (double)h / iters;
+  if (SPIN) warps_per_smsp = 1;   // one measured warp per SMSP, the others spin
   printf("%-40s warps/SMSP=%d : %7.1f clk per 64-pair row  = %.2f clk per pair per warp, %.2f per pair per SMSP\n", name,
          warps_per_smsp, per_tile, per_tile / 64, per_tile / 64 / warps_per_smsp);
   cudaFree(out); cudaFree(cyc);
@@ -88,5 +112,7 @@ int main() {
     run<1 | 2 | 8>("FFMA2 + MUFU + F2FP (no row sum)", w, in);
     run<15>("full mix (FFMA2, 2 MUFU, FADD2, F2FP)", w, in);
   }
+  // one measured warp per SMSP + one warp per SMSP spinning on an mbarrier (255 registers per thread cap the block at 256)
+  run<15, true>("full mix + 1 spinning warp/SMSP", 2, in);
   return 0;
 }
