@@ -95,6 +95,30 @@ constexpr float kFastSumLimit = 32768.0f;
 #ifndef FA_ABLATE
 #define FA_ABLATE 0
 #endif
+// TMEM protocol.  1 (default): ONE score buffer shared by the two Q tiles, P in columns of its own:
+//   S (128) | P0 (64) | P1 (64) | O0 (D) | O1 (D).  A softmax warpgroup copies its S into registers at once (66 clk) and
+//   hands the buffer back (s_free), so QK^T of step j+1 is issued while the softmax of step j is still running instead of
+//   behind P V of step j: the score product leaves the softmax -> PV -> QK^T -> softmax chain (1200 of the 3000 clk of a
+//   step) and the kernel becomes tensor-pipe / MUFU bound.
+// 0: round-1 protocol, S0 | S1 | O0 | O1 with P written over the first 64 columns of its own S tile (QK^T of step j+1 has
+//   to wait for P V of step j).  The precise mode (P as hi + lo operands, 128 P columns per tile) always uses it.
+#ifndef FA_SHARED_S
+#define FA_SHARED_S 1
+#endif
+#ifndef FA_SHARED_S_MAX_D
+#define FA_SHARED_S_MAX_D 64
+#endif
+#ifndef FA_FAST_MIN_D
+#define FA_FAST_MIN_D 128
+#endif
+// 1: the MMA warp polls its barriers with mbarrier.test_wait in a tight loop instead of the suspending try_wait
+// 1: the epilogue warpgroup's item-long wait for 1/l is a named barrier (no polling) instead of an mbarrier
+#ifndef FA_EP_NAMED_BAR
+#define FA_EP_NAMED_BAR 1
+#endif
+#ifndef FA_MMA_SPIN
+#define FA_MMA_SPIN 0
+#endif
 #ifndef FA_FAST_SOFTMAX
 #define FA_FAST_SOFTMAX 1
 #endif
@@ -285,6 +309,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                     const __grid_constant__ CUtensorMap tmW, const FwdArgs a) {
   using T = FwdTraits<D>;
+  constexpr bool kSharedS = (FA_SHARED_S != 0) && !kPrecise && D <= FA_SHARED_S_MAX_D;
+  // TMEM columns (fp32 columns; P is 16-bit, 64 columns per tile)
+  constexpr uint32_t kColS1 = kSharedS ? 0u : uint32_t(kBlockN);              // S of tile 1 (tile 0: column 0)
+  constexpr uint32_t kColP0 = kSharedS ? uint32_t(kBlockN) : 0u;              // P of tile 0
+  constexpr uint32_t kColP1 = kSharedS ? uint32_t(kBlockN + kBlockN / 2) : uint32_t(kBlockN);
+  constexpr uint32_t kColO = 2u * kBlockN;                                    // O_i at kColO + i * D
   constexpr int kStages = T::kStages;
   constexpr uint32_t kTileBytes = T::kTileBytes;
   constexpr uint32_t kBoxBytes = T::kBoxBytes;
@@ -312,6 +342,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t bar_kv_empty = bars + 144 + 8 * kStages;  // [kStages]
   const uint32_t tmem_slot = bars + 144 + 16 * kStages;    // u32 written by tcgen05.alloc
   const uint32_t bar_pv_part = bars + 384;                 // [2]  MMA -> softmax (first part of a PV has landed)
+  const uint32_t bar_s_free = bars + 400;                  // softmax -> MMA (shared S buffer copied into registers; 128 arrivals)
   const uint32_t bar_clc_full = bars + 416;                // [2]  CLC response landed (16 tx bytes)
   const uint32_t bar_clc_empty = bars + 432;               // [2]  all 14 consumer warps have read the response
   const uint32_t clc_resp = bars + 448;                    // [2] x 16 B
@@ -354,6 +385,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(bar_p_full + 16 * i, 128);
       mbar_init(bar_p_full + 16 * i + 8, 128);
     }
+    mbar_init(bar_s_free, 128);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_kv_full + 8 * s, 1);
       mbar_init(bar_kv_empty + 8 * s, 1);
@@ -437,6 +469,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // the tcgen05.mma / tcgen05.commit instructions.  Keeping the flow warp-uniform lets the compiler
       // hold descriptors in uniform registers: the issue cost per MMA must stay well under the 64
       // cycles one 128x128x16 MMA takes on the tensor pipe.
+      auto mbar_wait = [&](uint32_t bar, uint32_t parity, int tag) {
+        if (FA_MMA_SPIN) fa::mbar_wait_spin(bar, parity, tag); else fa::mbar_wait(bar, parity, tag);
+      };
       const uint32_t hi_qk = uint32_t(a.desc_hi_qk >> 32), hi_v = uint32_t(a.desc_hi_v >> 32);
       const uint32_t lo_qk = uint32_t(a.desc_hi_qk), lo_v = uint32_t(a.desc_hi_v);
       const uint32_t idesc_qk = a.idesc_qk, idesc_pv = a.idesc_pv;
@@ -444,7 +479,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto issue_qk = [&](int i, int stage, uint32_t bar_done, uint32_t bar_rel_a, uint32_t bar_rel_b) {
         const uint32_t a_lo = lo_qk | ((sQ + i * kTileBytes) >> 4);
         const uint32_t b_lo = lo_qk | ((sKV + stage * kTileBytes) >> 4);
-        const uint32_t d_tmem = tmem_base + i * kBlockN;
+        const uint32_t d_tmem = tmem_base + (i ? kColS1 : 0u);
         if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < ((FA_ABLATE & 64) ? D / 32 : D / 16); ++k) {
@@ -461,8 +496,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // soon as the softmax warpgroup has published those columns of P, while it is still exponentiating the rest.
       auto issue_pv = [&](int i, int stage, bool acc, uint32_t parity, uint32_t bar_done, uint32_t bar_release) {
         const uint32_t b_lo = lo_v | ((sKV + stage * kTileBytes) >> 4);
-        const uint32_t p_tmem = tmem_base + i * kBlockN;           // P aliases S_i
-        const uint32_t d_tmem = tmem_base + 2 * kBlockN + i * D;   // O_i
+        const uint32_t p_tmem = tmem_base + (i ? kColP1 : kColP0);
+        const uint32_t d_tmem = tmem_base + kColO + i * D;          // O_i
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(bar_p_full + 16 * i + 8 * h, parity, 212 + 2 * i + h);
@@ -493,6 +528,17 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t cnt[2] = {0u, 0u};     // S/P/O phase counters per tile (one per (tile, j) step, across items)
       uint32_t nq[2] = {0u, 0u};      // Q_i tiles consumed so far
       uint32_t ne[2] = {0u, 0u};      // epilogues of tile i started before this item (items where the tile is valid)
+      uint32_t nqk = 0;               // shared-S protocol: score products issued so far (each one is followed by one s_free)
+      // shared-S protocol: the buffer is free again once the softmax warpgroup that owns the previous S has it in registers
+      auto wait_s_free = [&]() {
+        if constexpr (kSharedS) {
+          if (nqk > 0) {
+            mbar_wait(bar_s_free, (nqk - 1u) & 1u, 230);
+            tc_fence_after();
+          }
+          ++nqk;
+        }
+      };
       int w = blockIdx.x;
       for (int t = 0; w >= 0; ++t) {
         const WorkItem wi = get_item<kCausal>(a, w);
@@ -504,11 +550,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (n_t0 > 0) {
             mbar_wait(bar_q_full, nq[0] & 1u, 201);
             tc_fence_after();
+            wait_s_free();
             issue_qk(0, stage_of(it0), bar_s_full, n_t1 > 0 ? 0u : rel, n_t0 == 1 ? bar_q_empty : 0u);
           }
           if (n_t1 > 0) {
             mbar_wait(bar_q_full + 8, nq[1] & 1u, 202);
             tc_fence_after();
+            wait_s_free();
             issue_qk(1, stage_of(it0), bar_s_full + 8, rel, n_t1 == 1 ? bar_q_empty + 8 : 0u);
           }
         }
@@ -521,19 +569,40 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t rel_k = bar_kv_empty + 8 * stage_of(it_k);
           // n_t1 >= n_t0 whenever both tiles exist (the second tile sits lower in the causal triangle);
           // tile 1 is absent (n_t1 == 0) only for a ragged last block.
-          if (j < n_t0) {
-            // the first PV of an item overwrites O_0: the epilogue must have read the previous item's O_0
-            if (j == 0) mbar_wait(bar_o_free, (ne[0] & 1u) ^ 1u, 220);
-            issue_pv(0, stage_of(it_v), j > 0, (cnt[0] + j) & 1u, bar_o_full, j < n_t1 ? 0u : rel_v);
+          if constexpr (kSharedS) {
+            // QK^T of step j+1 goes first: it only needs the score buffer (the other tile's softmax has copied its S
+            // out), not this tile's P V of step j, so S_i(j+1) is waiting when the softmax of S_i(j) ends.
+            if (j + 1 < n_t0) {
+              wait_s_free();
+              issue_qk(0, stage_of(it_k), bar_s_full, j + 1 < n_t1 ? 0u : rel_k, j + 2 == n_t0 ? bar_q_empty : 0u);
+            }
+            if (j < n_t0) {
+              if (j == 0) mbar_wait(bar_o_free, (ne[0] & 1u) ^ 1u, 220);
+              issue_pv(0, stage_of(it_v), j > 0, (cnt[0] + j) & 1u, bar_o_full, j < n_t1 ? 0u : rel_v);
+            }
+            if (j + 1 < n_t1) {
+              wait_s_free();
+              issue_qk(1, stage_of(it_k), bar_s_full + 8, rel_k, j + 2 == n_t1 ? bar_q_empty + 8 : 0u);
+            }
+            if (j < n_t1) {
+              if (j == 0) mbar_wait(bar_o_free + 8, (ne[1] & 1u) ^ 1u, 221);
+              issue_pv(1, stage_of(it_v), j > 0, (cnt[1] + j) & 1u, bar_o_full + 8, rel_v);
+            }
+          } else {
+            if (j < n_t0) {
+              // the first PV of an item overwrites O_0: the epilogue must have read the previous item's O_0
+              if (j == 0) mbar_wait(bar_o_free, (ne[0] & 1u) ^ 1u, 220);
+              issue_pv(0, stage_of(it_v), j > 0, (cnt[0] + j) & 1u, bar_o_full, j < n_t1 ? 0u : rel_v);
+            }
+            if (j + 1 < n_t0)
+              issue_qk(0, stage_of(it_k), bar_s_full, j + 1 < n_t1 ? 0u : rel_k, j + 2 == n_t0 ? bar_q_empty : 0u);
+            if (j < n_t1) {
+              if (j == 0) mbar_wait(bar_o_free + 8, (ne[1] & 1u) ^ 1u, 221);
+              issue_pv(1, stage_of(it_v), j > 0, (cnt[1] + j) & 1u, bar_o_full + 8, rel_v);
+            }
+            if (j + 1 < n_t1)
+              issue_qk(1, stage_of(it_k), bar_s_full + 8, rel_k, j + 2 == n_t1 ? bar_q_empty + 8 : 0u);
           }
-          if (j + 1 < n_t0)
-            issue_qk(0, stage_of(it_k), bar_s_full, j + 1 < n_t1 ? 0u : rel_k, j + 2 == n_t0 ? bar_q_empty : 0u);
-          if (j < n_t1) {
-            if (j == 0) mbar_wait(bar_o_free + 8, (ne[1] & 1u) ^ 1u, 221);
-            issue_pv(1, stage_of(it_v), j > 0, (cnt[1] + j) & 1u, bar_o_full + 8, rel_v);
-          }
-          if (j + 1 < n_t1)
-            issue_qk(1, stage_of(it_k), bar_s_full + 8, rel_k, j + 2 == n_t1 ? bar_q_empty + 8 : 0u);
         }
         it0 += 2 * n_max;
         cnt[0] += uint32_t(n_t0);
@@ -569,8 +638,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int i = 0; i < 2; ++i) {
         if (!(i ? wi.valid1 : wi.valid0)) continue;
         const int n_i = i ? wi.n_t1 : wi.n_t0;
-        const uint32_t tO = tmem_base + lane_addr + 2 * kBlockN + i * D;
+        const uint32_t tO = tmem_base + lane_addr + kColO + i * D;
+#if FA_EP_NAMED_BAR
+        // the epilogue warpgroup waits for almost a whole work item here: on a hardware named barrier (the softmax
+        // warpgroup arrives, this one syncs) it does not poll, so it leaves its SMSP's issue slots to the softmax warps
+        asm volatile("bar.sync %0, %1;" ::"r"(3 + i), "r"(256) : "memory");
+#else
         mbar_wait(bar_ep_full + 8 * i, ne[i] & 1u, 400 + i);
+#endif
         ++ne[i];
         float inv_l;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(inv_l) : "r"(s_inv_l + uint32_t(i * 128 + row_in_tile) * 4u) : "memory");
@@ -640,8 +715,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int wl = warp & 3;           // warp within the warpgroup == TMEM lane quarter
     const int row_in_tile = wl * 32 + lane;
     const uint32_t lane_addr = uint32_t(wl * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + i * kBlockN;
-    const uint32_t tO = tmem_base + lane_addr + 2 * kBlockN + i * D;
+    const uint32_t tS = tmem_base + lane_addr + (i ? kColS1 : 0u);
+    const uint32_t tP = tmem_base + lane_addr + (i ? kColP1 : kColP0);   // 16-bit P, 64 columns (+ 64 of P_lo in precise mode)
+    const uint32_t tO = tmem_base + lane_addr + kColO + i * D;
     const uint32_t b_s_full = bar_s_full + 8 * i;
     const uint32_t b_p_full = bar_p_full + 16 * i;
     const uint32_t b_o_full = bar_o_full + 8 * i;
@@ -680,6 +756,17 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, sr[q]);
         tmem_wait_ld();
+        if constexpr (kSharedS) {
+          // S is in registers: hand the score buffer to the other tile's QK^T ...
+          tc_fence_before();
+          mbar_arrive(bar_s_free);
+          // ... and before P of this step overwrites P of the previous one, P V of the previous step must have read it
+          // (with P written over its own S tile this was implied by S(j) being there at all)
+          if (cnt + uint32_t(j) > 0u) {
+            mbar_wait(b_o_full, par ^ 1u, 340 + i);
+            tc_fence_after();
+          }
+        }
         if (row_in_tile == 0 && t == 0) FA_TRACE_EV(j, 4 * i + 1);
 
         const float2 c2 = make_float2(c, c);
@@ -709,8 +796,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               pl[k] = pack2<kBF16>(__fadd2_rn(pv, make_float2(-hi.x, -hi.y)));
             }
           }
-          tmem_st16(tS + q * 16, pk);
-          if constexpr (kPrecise) tmem_st16(tS + kBlockN / 2 + q * 16, pl);   // P_lo over columns 64..127
+          tmem_st16(tP + q * 16, pk);
+          if constexpr (kPrecise) tmem_st16(tP + kBlockN / 2 + q * 16, pl);   // P_lo over columns 64..127
         };
         auto publish = [&](int part, bool already) {   // P columns written so far are visible to the MMA warp
           if (!(FA_ABLATE & 16)) tmem_wait_st();
@@ -760,7 +847,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         //     exponentiate the second part again.
         bool done = false;
         bool arrived0 = false, arrived1 = false;   // this thread's arrivals on p_full[0 / 1] for this tile
-        if (FA_FAST_SOFTMAX && D == 128 && !kPrecise && j > 0 && !masked && !a.need_stats) {
+        if (FA_FAST_SOFTMAX && D >= FA_FAST_MIN_D && !kPrecise && j > 0 && !masked && !a.need_stats) {
           float2 neg_m2 = make_float2(-m_ref, -m_ref);     // finite: the row saw a whole unmasked tile before
           float2 ls0[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
           float2 ls1[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -859,7 +946,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(bar_ep_empty + 8 * i, (ne & 1u) ^ 1u, 330 + i);   // slot of the previous hand-off consumed
       ++ne;
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_inv_l + uint32_t(i * 128 + row_in_tile) * 4u), "f"(inv_l) : "memory");
+#if FA_EP_NAMED_BAR
+      asm volatile("bar.arrive %0, %1;" ::"r"(3 + i), "r"(256) : "memory");
+#else
       mbar_arrive(bar_ep_full + 8 * i);
+#endif
       const WorkItem wi = get_item<kCausal>(a, w_cur);   // recomputed here to keep it out of the hot loop's registers
       const int row = wi.q0 + i * kBlockM + row_in_tile;
       if (row < a.Nq) {

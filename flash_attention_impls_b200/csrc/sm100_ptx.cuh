@@ -85,6 +85,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
+// Same, polling with the non-suspending mbarrier.test_wait: reacts faster than try_wait's hardware-timed suspension at
+// the price of issue slots; for a warp that has its scheduler slot to itself.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (++spins > FA_WATCHDOG_SPINS) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- cluster launch control (CLC)
 // Blackwell's hardware work-stealing for persistent kernels: a running CTA asks the launch hardware to
 // cancel a CTA of the same grid that has not started yet and takes over its blockIdx.  The 16-byte
