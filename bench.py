@@ -249,6 +249,30 @@ def kernel_record(torch, fa, name, dev, peaks, steps):
             "l2": "L2 flushed (512 MB write) between timed iterations" if flush is not None else "inputs exceed L2"}
 
 
+def zero_input_record(torch, fa, name, dev, peaks, steps, real_tflops):
+    """The same launch on all-zero inputs.  Zero operands do not toggle the tensor pipe's datapath, the GPU stays far
+    below its power limit and the SM clock at its maximum, so this figure is the kernel's CYCLE count; the headline (random
+    inputs) is what power management leaves of it.  Explains the roofline fraction, is not a throughput claim."""
+    B, H, N, d, dtype_name, causal = WORKLOADS[name]
+    dtype = torch.bfloat16 if dtype_name == "bf16" else torch.float16
+    q = torch.zeros((B, H, N, d), dtype=dtype, device=dev)
+    k, v, o = torch.zeros_like(q), torch.zeros_like(q), torch.empty_like(q)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+
+    def step():
+        fa.attention_forward(q, k, v, causal=causal, out=o, lse=lse)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    total, per = timed_steps(torch, step, steps)
+    ms = sum(per) / len(per)
+    tf = flops_of(B, H, N, d, causal) / (ms * 1e-3) * 1e-12
+    return {"workload": name + " shape, all-zero inputs (SM clock stays at max: cycle-domain rate)", "steps": steps,
+            "launch_ms_mean": ms, "launch_ms_min": per[0], "tflops": tf, "frac_of_measured_tensor_peak": tf / peaks["tflops"],
+            "random_over_zero": real_tflops / tf,
+            "note": "random_over_zero = headline kernel rate / this rate: what the power limit costs on real data"}
+
+
 def backward_record(torch, fa, dev, peaks, steps):
     """SURVEY.md section 8f.4 as a sub-record: fa_b200_backward (delta pre-pass + dQ kernel + dK/dV kernel) at the c3 shape.
     FLOPs in the usual 5-product convention, 10*B*H*N^2*d (the two kernels execute 7 products: S and dP are recomputed)."""
@@ -436,6 +460,9 @@ def main():
     if not args.no_sub and args.workload == "c3":
         sub_steps = max(3, min(args.steps, 10))
         if world == 1:
+            # first, after a pause (it is meant to show the kernel with the clock at its maximum, not after a hot run)
+            time.sleep(1.0)
+            sub["c3_zero_inputs"] = zero_input_record(torch, fa, "c3", dev, peaks, sub_steps, roofline["achieved"])
             for name in ("c2", "c4"):
                 sub[name] = kernel_record(torch, fa, name, dev, peaks, max(sub_steps, 20))
             sub["backward_c3"] = backward_record(torch, fa, dev, peaks, sub_steps)
