@@ -65,7 +65,9 @@ typedef struct fa_b200_params {
   void* O;           /* [B,H,N,d]    dtype */
   float* lse;        /* optional [B,H,N]: natural-log logsumexp of the scaled scores, = m + ln(l) */
   float* l;          /* optional [B,H,N]: sum_j exp(s_ij - m_i)    (flashAttention.cu:115-120,137) */
-  float* m;          /* optional [B,H,N]: max_j s_ij, s = q.k*scale (flashAttention.cu:138)        */
+  float* m;          /* optional [B,H,N]: max_j s_ij, s = q.k*scale (flashAttention.cu:138)
+                        (asking for l or m keeps the kernel on its exact-row-max path for every tile; O and lse alone
+                        let it skip the row-max pass where a tile provably needs none - same results to rounding) */
   int B, H, N, d;
   int N_kv;          /* 0 => N (self-attention, the only case the reference has) */
   int dtype;         /* enum fa_b200_dtype */
@@ -86,8 +88,10 @@ typedef struct fa_b200_params {
   void* stream;      /* cudaStream_t; NULL => legacy default stream, as in the reference */
   /* Optional device scratch for split-KV scheduling: launches with far fewer (b,h,256-row) work items than SMs
    * (e.g. the reference's (1,1,N,64) sweep, report/pmph-a6.tex:282-286) are cut along the key axis into partial
-   * results that a second kernel combines with their logsumexp.  Size it with fa_b200_workspace_bytes(); NULL or
-   * too small => the plain single-pass schedule.  The callee still allocates nothing. */
+   * results that a second kernel combines with their logsumexp; so is the last, at most half-filled wave of a
+   * non-causal launch of long equal items (c3 sharded over 8 GPUs: 512 items on 148 SMs).  Size it with
+   * fa_b200_workspace_bytes(); NULL or too small => the plain single-pass schedule.  The callee still allocates
+   * nothing. */
   void* workspace;
   size_t workspace_bytes;
   /* 1: feed P to the P.V tensor-core product as two 16-bit operands (P = P_hi + P_lo, the rounding residual),
