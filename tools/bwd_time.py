@@ -19,6 +19,8 @@ if "--one" in sys.argv:          # short run for an ncu capture: the c3 shape on
 for (B, H, N, d, dtype, causal) in SHAPES:
     g = torch.Generator(device=dev); g.manual_seed(1)
     q, k, v, do = (torch.randn((B, H, N, d), generator=g, device=dev).to(dtype) for _ in range(4))
+    if "--zeros" in sys.argv:    # cycle-domain timing: zero operands keep the GPU under its power limit, clock at max
+        q, k, v, do = (torch.zeros_like(t) for t in (q, k, v, do))
     o, lse = fa.attention_forward(q, k, v, causal=causal)
     for _ in range(1 if "--one" in sys.argv else 3):
         fa.attention_backward(q, k, v, o, lse, do, causal=causal)
@@ -33,4 +35,4 @@ for (B, H, N, d, dtype, causal) in SHAPES:
     ms = e0.elapsed_time(e1) / n
     fl = 10.0 * B * H * N * N * d / (2 if causal else 1)
     print(f"BWD_TIMING B={B} H={H} N={N} d={d} {str(dtype).split('.')[-1]} causal={int(causal)}: {ms:.3f} ms "
-          f"-> {fl / ms * 1e-9:.1f} TFLOP/s (5-product convention)", flush=True)
+          f"-> {fl / ms * 1e-9:.1f} TFLOP/s (5-product convention){' [zero inputs]' if '--zeros' in sys.argv else ''}", flush=True)
