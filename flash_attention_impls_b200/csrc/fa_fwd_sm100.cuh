@@ -105,6 +105,18 @@ constexpr float kFastSumLimit = 32768.0f;
 #ifndef FA_SHARED_S
 #define FA_SHARED_S 1
 #endif
+// 1: TWO MMA issuer warps, one per Q tile (warps 13 and 15), each walking only its own tile's chain (S_i -> softmax ->
+//   P_i V -> Q_i K^T) so that a wait for the other tile's P never holds up this tile's MMAs and nothing is serialised at a
+//   work-item boundary; K/V stages are released by two arrivals (an issuer that does not use a stage arrives for it after
+//   seeing it filled); d <= 64 TMEM map S0 | S1 | P0 | P1 | O0 | O1.  Correct (parity list green) but MEASURED MUCH SLOWER at
+//   d = 128: c3 on zero inputs 1615 -> 1168 TFLOP/s (3.77 ms, the same on random inputs), c2 523 -> 485, d = 64 long
+//   sequences unchanged (873 -> 869): MMAs of two issuing threads interleave on the tensor pipe, and every switch between
+//   accumulator tiles costs what a fixed order pays only four times per step.  Kept as an A/B switch, default 0
+//   (profiles/r02_fast_softmax_ab.log).
+// 0 (default): one issuer (warp 13) for both tiles, fixed interleaved order; d <= 64 uses the shared-S map (FA_SHARED_S).
+#ifndef FA_TWO_ISSUERS
+#define FA_TWO_ISSUERS 0
+#endif
 #ifndef FA_SHARED_S_MAX_D
 #define FA_SHARED_S_MAX_D 64
 #endif
@@ -309,12 +321,15 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                     const __grid_constant__ CUtensorMap tmW, const FwdArgs a) {
   using T = FwdTraits<D>;
-  constexpr bool kSharedS = (FA_SHARED_S != 0) && !kPrecise && D <= FA_SHARED_S_MAX_D;
+  constexpr bool kTwoIssuers = (FA_TWO_ISSUERS != 0);
+  constexpr bool kSepP = kTwoIssuers && !kPrecise && D <= FA_SHARED_S_MAX_D;     // S0 | S1 | P0 | P1 | O0 | O1
+  constexpr bool kSharedS = !kTwoIssuers && (FA_SHARED_S != 0) && !kPrecise && D <= FA_SHARED_S_MAX_D;
   // TMEM columns (fp32 columns; P is 16-bit, 64 columns per tile)
   constexpr uint32_t kColS1 = kSharedS ? 0u : uint32_t(kBlockN);              // S of tile 1 (tile 0: column 0)
-  constexpr uint32_t kColP0 = kSharedS ? uint32_t(kBlockN) : 0u;              // P of tile 0
-  constexpr uint32_t kColP1 = kSharedS ? uint32_t(kBlockN + kBlockN / 2) : uint32_t(kBlockN);
-  constexpr uint32_t kColO = 2u * kBlockN;                                    // O_i at kColO + i * D
+  constexpr uint32_t kColP0 = kSharedS ? uint32_t(kBlockN) : (kSepP ? 2u * kBlockN : 0u);               // P of tile 0
+  constexpr uint32_t kColP1 = kSharedS ? uint32_t(kBlockN + kBlockN / 2) : (kSepP ? 2u * kBlockN + kBlockN / 2 : uint32_t(kBlockN));
+  constexpr uint32_t kColO = kSepP ? 3u * kBlockN : 2u * kBlockN;             // O_i at kColO + i * D
+  static_assert(kColO + 2 * D <= 512, "TMEM map does not fit");
   constexpr int kStages = T::kStages;
   constexpr uint32_t kTileBytes = T::kTileBytes;
   constexpr uint32_t kBoxBytes = T::kBoxBytes;
@@ -342,7 +357,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t bar_kv_empty = bars + 144 + 8 * kStages;  // [kStages]
   const uint32_t tmem_slot = bars + 144 + 16 * kStages;    // u32 written by tcgen05.alloc
   const uint32_t bar_pv_part = bars + 384;                 // [2]  MMA -> softmax (first part of a PV has landed)
-  const uint32_t bar_s_free = bars + 400;                  // softmax -> MMA (shared S buffer copied into registers; 128 arrivals)
+  const uint32_t bar_s_free = bars + 400;                  // [2] softmax -> MMA (S copied into registers; 128 arrivals; shared-S map: one)
   const uint32_t bar_clc_full = bars + 416;                // [2]  CLC response landed (16 tx bytes)
   const uint32_t bar_clc_empty = bars + 432;               // [2]  all 14 consumer warps have read the response
   const uint32_t clc_resp = bars + 448;                    // [2] x 16 B
@@ -350,7 +365,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t kClcConsumers = 14;   // producer lane + MMA warp + 8 softmax warps + 4 epilogue warps
+  constexpr uint32_t kClcConsumers = kTwoIssuers ? 15 : 14;   // producer lane + MMA warp(s) + 8 softmax warps + 4 epilogue warps
   // Every role walks the same item sequence: blockIdx.x first, then whatever the scheduler lane stole.
   // The response for item t+1 is requested at the start of item t into slot (t+1)&1 and read by every
   // consumer when it has finished item t.
@@ -386,9 +401,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(bar_p_full + 16 * i + 8, 128);
     }
     mbar_init(bar_s_free, 128);
+    mbar_init(bar_s_free + 8, 128);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_kv_full + 8 * s, 1);
-      mbar_init(bar_kv_empty + 8 * s, 1);
+      mbar_init(bar_kv_empty + 8 * s, kTwoIssuers ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_clc_full + 8 * s, 1);
@@ -463,8 +479,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       __syncwarp();
-    } else if (warp == 13) {
-      // =========================== MMA issuer ===========================
+    } else if (warp == 13 || (kTwoIssuers && warp == 15)) {
+      // =========================== MMA issuer(s) ===========================
       // The whole warp runs the (uniform) control flow and the barrier waits; one elected lane issues
       // the tcgen05.mma / tcgen05.commit instructions.  Keeping the flow warp-uniform lets the compiler
       // hold descriptors in uniform registers: the issue cost per MMA must stay well under the 64
@@ -524,6 +540,78 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto stage_of = [&](int it) { return it % kStages; };
       auto phase_of = [&](int it) { return uint32_t((it / kStages) & 1); };
 
+      if constexpr (kTwoIssuers) {
+        // ---- one issuer per Q tile: warp 13 -> tile 0, warp 15 -> tile 1
+        const int i = (warp == 15) ? 1 : 0;
+        const uint32_t b_s_full = bar_s_full + 8 * i, b_o_full = bar_o_full + 8 * i, b_o_free = bar_o_free + 8 * i;
+        const uint32_t b_q_full = bar_q_full + 8 * i, b_q_empty = bar_q_empty + 8 * i, b_s_free = bar_s_free + 8 * i;
+        int it0 = 0;          // ring position of this item's K_0
+        uint32_t cnt = 0;     // S/P/O steps of this tile so far (across items)
+        uint32_t nq = 0;      // Q_i tiles consumed so far
+        uint32_t ne = 0;      // epilogues of this tile started before this item
+        // a stage this tile does not read still needs this issuer's arrival; arriving only after the stage has been seen
+        // filled keeps the arrival in the right phase of kv_empty
+        auto pass_stage = [&](int it) {
+          mbar_wait(bar_kv_full + 8 * stage_of(it), phase_of(it), 240);
+          if (lane == 0) mbar_arrive(bar_kv_empty + 8 * stage_of(it));
+          __syncwarp();
+        };
+        // S_i of step `step` (counted across items) is in the softmax warpgroup's registers
+        auto wait_s_copied = [&](uint32_t step) {
+          if constexpr (kSepP) {
+            mbar_wait(b_s_free, step & 1u, 231);
+            tc_fence_after();
+          }
+        };
+        int w = blockIdx.x;
+        for (int t = 0; w >= 0; ++t) {
+          const WorkItem wi = get_item<kCausal>(a, w);
+          const int n_i = i ? wi.n_t1 : wi.n_t0, n_max = wi.n_max;
+          const bool valid_i = i ? wi.valid1 : wi.valid0;
+          if (n_max > 0) {
+            if (n_i > 0) {      // S_i(0) = Q_i K_0^T
+              mbar_wait(bar_kv_full + 8 * stage_of(it0), phase_of(it0), 200);
+              mbar_wait(b_q_full, nq & 1u, 201 + i);
+              tc_fence_after();
+              if (cnt > 0) wait_s_copied(cnt - 1u);
+              issue_qk(i, stage_of(it0), b_s_full, bar_kv_empty + 8 * stage_of(it0), n_i == 1 ? b_q_empty : 0u);
+            } else {
+              pass_stage(it0);
+            }
+          }
+          for (int j = 0; j < n_max; ++j) {
+            const int it_v = it0 + 2 * j + 1, it_k = it0 + 2 * j + 2;
+            const bool has_next = (j + 1 < n_max);
+            auto next_qk = [&]() {
+              if (!has_next) return;
+              if (j + 1 < n_i) {
+                mbar_wait(bar_kv_full + 8 * stage_of(it_k), phase_of(it_k), 211);
+                wait_s_copied(cnt + uint32_t(j));
+                issue_qk(i, stage_of(it_k), b_s_full, bar_kv_empty + 8 * stage_of(it_k), j + 2 == n_i ? b_q_empty : 0u);
+              } else {
+                pass_stage(it_k);
+              }
+            };
+            if constexpr (kSepP) next_qk();      // P has columns of its own: the score product does not wait for P V(j)
+            if (j < n_i) {
+              mbar_wait(bar_kv_full + 8 * stage_of(it_v), phase_of(it_v), 210);
+              // the first PV of an item overwrites O_i: the epilogue must have read the previous item's O_i
+              if (j == 0) mbar_wait(b_o_free, (ne & 1u) ^ 1u, 220 + i);
+              issue_pv(i, stage_of(it_v), j > 0, (cnt + uint32_t(j)) & 1u, b_o_full, bar_kv_empty + 8 * stage_of(it_v));
+            } else {
+              pass_stage(it_v);
+            }
+            if constexpr (!kSepP) next_qk();     // P lies over S_i: Q_i K^T(j+1) follows P_i V(j)
+          }
+          it0 += 2 * n_max;
+          cnt += uint32_t(n_i);
+          nq += n_i > 0 ? 1u : 0u;
+          ne += valid_i ? 1u : 0u;
+          w = next_item(t + 1);
+          __syncwarp();
+          if (lane == 0) release_item_slot(t + 1);
+        }
+      } else {
       int it0 = 0;                    // ring position of this item's K_0
       uint32_t cnt[2] = {0u, 0u};     // S/P/O phase counters per tile (one per (tile, j) step, across items)
       uint32_t nq[2] = {0u, 0u};      // Q_i tiles consumed so far
@@ -615,6 +703,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
         if (lane == 0) release_item_slot(t + 1);
       }
+      }   // one issuer
     }
   } else if (warp >= 8) {
     // =========================== correction / epilogue warpgroup ===========================
@@ -756,10 +845,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int q = 0; q < 4; ++q) tmem_ld32(tS + q * 32, sr[q]);
         tmem_wait_ld();
-        if constexpr (kSharedS) {
-          // S is in registers: hand the score buffer to the other tile's QK^T ...
+        if constexpr (kSharedS || kSepP) {
+          // S is in registers: the score buffer may take the next score product (shared-S map: the other tile's) ...
           tc_fence_before();
-          mbar_arrive(bar_s_free);
+          mbar_arrive(bar_s_free + (kSepP ? 8 * i : 0));
           // ... and before P of this step overwrites P of the previous one, P V of the previous step must have read it
           // (with P written over its own S tile this was implied by S(j) being there at all)
           if (cnt + uint32_t(j) > 0u) {
