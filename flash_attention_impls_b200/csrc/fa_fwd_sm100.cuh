@@ -20,10 +20,15 @@
 //                   across items, so the next item's first tiles are prefetched)
 //     warp  13    : tcgen05.mma issuer (one elected lane): S_i = Q_i K_j^T -> TMEM, O_i += P_i V_j
 //     warp  14    : TMEM allocator / deallocator
-//   TMEM (512 columns): S0 | S1 | O0 | O1, fp32.  P (bf16/fp16) is written back over the first
+//   TMEM (512 columns), d = 128: S0 | S1 | O0 | O1, fp32; P (bf16/fp16) is written back over the first
 //   columns of its S tile and consumed by the PV MMA directly from TMEM (A-operand in TMEM).
+//   d <= 64: S | P0 | P1 | O0 | O1 - one score buffer shared by the two Q tiles (a softmax warpgroup copies
+//   its S into registers at once and hands the buffer back), P in columns of its own, so Q K^T of step j+1
+//   is issued before P V of step j (see FA_SHARED_S below).
 //   Online softmax runs in the log2 domain with a lazily updated reference max: O and l are only
-//   rescaled when the true row max has moved more than 2^8 above the reference max.
+//   rescaled when the true row max has moved more than 2^8 above the reference max; at d = 128, tiles
+//   that provably need no new reference max skip the row-max pass altogether (fast softmax path: the row sum
+//   of each published part of P bounds its entries; predicated barrier arrivals, redo on the exact path).
 //   The logsumexp (and the reference's l, m) are written with coalesced fp32 stores.
 #pragma once
 #include <cuda_bf16.h>
@@ -860,7 +865,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         const float2 c2 = make_float2(c, c);
         // p = 2^(s*c + neg_m) for the 32 keys of group q, with packed (2-wide) fp32 math; FA_EMU_PAIRS_OF_4 of every 4
-        // pairs take the polynomial path, the rest MUFU.EX2.  P (16-bit) goes over the first 64 columns of S.
+        // pairs take the polynomial path, the rest MUFU.EX2.  P (16-bit) goes to tP (over S_i, or columns of its own).
         auto exp_group = [&](int q, const float2 neg_m2, float2 (&lsum2)[4], const float2 neg_late2, int late_from = 16) {
           uint32_t pk[16];
           [[maybe_unused]] uint32_t pl[16];
