@@ -148,7 +148,7 @@ fa_bwd_dkdv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
   auto phase_of = [&](int t) { return uint32_t((t / kSlots) & 1); };
   const uint32_t s_stats = bars + 256;         // [2 halves][2 stages][lse2(64) | delta(64)] fp32 = 2 KB
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // lane-0 shuffle: the compiler then knows it is warp-uniform
   const int lane = threadIdx.x & 31;
   const int f = int(blockIdx.x % uint32_t(a.kv_tiles));      // this CTA's K/V tile
   const int bh = int(blockIdx.x / uint32_t(a.kv_tiles));
@@ -454,7 +454,7 @@ fa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   auto slot_of = [&](int t) { return uint32_t(t % kSlots); };
   auto phase_of = [&](int t) { return uint32_t((t / kSlots) & 1); };
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // lane-0 shuffle: the compiler then knows it is warp-uniform
   const int lane = threadIdx.x & 31;
   const int f = int(blockIdx.x % uint32_t(a.q_tiles));       // this CTA's query tile
   const int bh = int(blockIdx.x / uint32_t(a.q_tiles));

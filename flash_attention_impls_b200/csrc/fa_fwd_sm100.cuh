@@ -119,6 +119,10 @@ constexpr float kFastSumLimit = 32768.0f;
 //   accumulator tiles costs what a fixed order pays only four times per step.  Kept as an A/B switch, default 0
 //   (profiles/r02_fast_softmax_ab.log).
 // 0 (default): one issuer (warp 13) for both tiles, fixed interleaved order; d <= 64 uses the shared-S map (FA_SHARED_S).
+// 1: warp index and work-item ids pass through __shfl_sync(.., 0) so that the compiler knows they are warp-uniform
+#ifndef FA_UNIFORM_HINT
+#define FA_UNIFORM_HINT 1
+#endif
 #ifndef FA_TWO_ISSUERS
 #define FA_TWO_ISSUERS 0
 #endif
@@ -368,17 +372,21 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t clc_resp = bars + 448;                    // [2] x 16 B
   const uint32_t s_inv_l = bars + 512;                     // [2 tiles][128 rows] fp32
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a lane-0 shuffle: tells the compiler it is warp-uniform, so everything derived from it (tile
+  // index, TMEM lane quarter, barrier addresses) can live in uniform registers instead of being recomputed from
+  // threadIdx after every barrier wait
+  const int warp = FA_UNIFORM_HINT ? __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0) : int(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kClcConsumers = kTwoIssuers ? 15 : 14;   // producer lane + MMA warp(s) + 8 softmax warps + 4 epilogue warps
   // Every role walks the same item sequence: blockIdx.x first, then whatever the scheduler lane stole.
   // The response for item t+1 is requested at the start of item t into slot (t+1)&1 and read by every
   // consumer when it has finished item t.
-  auto next_item = [&](int t_next) -> int {
+  auto next_item = [&](int t_next, bool whole_warp = true) -> int {
     const uint32_t slot = uint32_t(t_next & 1);
     mbar_wait(bar_clc_full + 8 * slot, uint32_t((t_next - 1) >> 1) & 1u, 500);   // use k = (t_next-1)/2 of the slot
     const int id = clc_decode(clc_resp + 16 * slot);
-    return id;
+    // same value in every lane: say so (not for the producer, which calls this from a single lane)
+    return (FA_UNIFORM_HINT && whole_warp) ? __shfl_sync(0xffffffffu, id, 0) : id;
   };
   auto release_item_slot = [&](int t_next) {   // one arrival per consumer warp, after all its lanes have read
     mbar_arrive(bar_clc_empty + 8 * uint32_t(t_next & 1));
@@ -479,7 +487,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               }
             }
           }
-          w = next_item(t + 1);
+          w = next_item(t + 1, false);
           release_item_slot(t + 1);
         }
       }
