@@ -219,6 +219,14 @@ __device__ __forceinline__ float2 ex2_emulated(float2 x) {
 #ifndef FA_EMU_PAIRS_OF_4
 #define FA_EMU_PAIRS_OF_4 0
 #endif
+// ... and, of every 8 pairs, for head dims <= 64 (instantiations 32 / 64), where the MUFU.EX2 unit, not the tensor pipe, is
+// the bound (2 exponentials per MMA clock).  Round 2, after the uniform-register hints had taken the address arithmetic off the
+// softmax warps: 2 of 8 -> 4,32,8192,64 900 -> 971 TFLOP/s on zero inputs, 895 -> 963 on Set S (cuDNN: 978), causal 847 -> 875,
+// c2 543 -> 555; 4 of 8 -> 879 (profiles/r02_fast_softmax_ab.log).  At d = 128 25 % is +0.7 % in cycles and -7 % on real data
+// (the extra FMA-pipe work costs power), so FA_EMU_PAIRS_OF_4 stays 0.
+#ifndef FA_EMU_PAIRS_OF_8_D64
+#define FA_EMU_PAIRS_OF_8_D64 2
+#endif
 
 // P is published to the MMA warp in two parts: the first FA_P_FIRST_Q groups of 32 keys, then the rest.  The part
 // that is published last sits on the softmax -> PV -> QK^T -> softmax chain: with 2 (halves) four PV MMAs (256 clk at
@@ -882,7 +890,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float2 x = make_float2(__uint_as_float(sr[q][2 * k]), __uint_as_float(sr[q][2 * k + 1]));
             if (!(FA_ABLATE & 2)) x = __ffma2_rn(x, c2, k < late_from ? neg_m2 : neg_late2);
             float2 pv;
-            if ((k & 3) < FA_EMU_PAIRS_OF_4) {
+            if (D <= 64 ? ((k & 7) < FA_EMU_PAIRS_OF_8_D64) : ((k & 3) < FA_EMU_PAIRS_OF_4)) {
               pv = ex2_emulated(x);
             } else if ((FA_ABLATE & 4) && (k & 1)) {
               pv = x;
