@@ -100,48 +100,56 @@ constexpr float kFastSumLimit = 32768.0f;
 #ifndef FA_ABLATE
 #define FA_ABLATE 0
 #endif
-// TMEM protocol.  1 (default): ONE score buffer shared by the two Q tiles, P in columns of its own:
-//   S (128) | P0 (64) | P1 (64) | O0 (D) | O1 (D).  A softmax warpgroup copies its S into registers at once (66 clk) and
-//   hands the buffer back (s_free), so QK^T of step j+1 is issued while the softmax of step j is still running instead of
-//   behind P V of step j: the score product leaves the softmax -> PV -> QK^T -> softmax chain (1200 of the 3000 clk of a
-//   step) and the kernel becomes tensor-pipe / MUFU bound.
-// 0: round-1 protocol, S0 | S1 | O0 | O1 with P written over the first 64 columns of its own S tile (QK^T of step j+1 has
-//   to wait for P V of step j).  The precise mode (P as hi + lo operands, 128 P columns per tile) always uses it.
+// ---- compile-time switches (defaults = the shipped kernel; the others exist for interleaved A/B builds, `make variant`)
+//
+// FA_SHARED_S / FA_SHARED_S_MAX_D - TMEM protocol for head dims <= FA_SHARED_S_MAX_D (default 64):
+//   ONE score buffer shared by the two Q tiles, P in columns of its own:  S (128) | P0 (64) | P1 (64) | O0 (D) | O1 (D).
+//   A softmax warpgroup copies its S into registers at once (66 clk) and hands the buffer back (s_free), so QK^T of step
+//   j+1 is issued while the softmax of step j is still running instead of behind P V of step j: the score product leaves
+//   the softmax -> PV -> QK^T -> softmax chain.  Larger head dims (and the precise mode at any d, which needs 128 P
+//   columns per tile) keep the round-1 protocol S0 | S1 | O0 | O1 with P written over the first 64 columns of its own S
+//   tile; at d = 128 the shared buffer serialises the two tiles' QK^T through the copy-out hand-offs and measured slower
+//   (1617 -> 1534 TFLOP/s on zero inputs; +1.4 % after the uniformity hints, within noise on real data).
 #ifndef FA_SHARED_S
 #define FA_SHARED_S 1
-#endif
-// 1: TWO MMA issuer warps, one per Q tile (warps 13 and 15), each walking only its own tile's chain (S_i -> softmax ->
-//   P_i V -> Q_i K^T) so that a wait for the other tile's P never holds up this tile's MMAs and nothing is serialised at a
-//   work-item boundary; K/V stages are released by two arrivals (an issuer that does not use a stage arrives for it after
-//   seeing it filled); d <= 64 TMEM map S0 | S1 | P0 | P1 | O0 | O1.  Correct (parity list green) but MEASURED MUCH SLOWER at
-//   d = 128: c3 on zero inputs 1615 -> 1168 TFLOP/s (3.77 ms, the same on random inputs), c2 523 -> 485, d = 64 long
-//   sequences unchanged (873 -> 869): MMAs of two issuing threads interleave on the tensor pipe, and every switch between
-//   accumulator tiles costs what a fixed order pays only four times per step.  Kept as an A/B switch, default 0
-//   (profiles/r02_fast_softmax_ab.log).
-// 0 (default): one issuer (warp 13) for both tiles, fixed interleaved order; d <= 64 uses the shared-S map (FA_SHARED_S).
-// 1: warp index and work-item ids pass through __shfl_sync(.., 0) so that the compiler knows they are warp-uniform
-#ifndef FA_UNIFORM_HINT
-#define FA_UNIFORM_HINT 1
-#endif
-#ifndef FA_TWO_ISSUERS
-#define FA_TWO_ISSUERS 0
 #endif
 #ifndef FA_SHARED_S_MAX_D
 #define FA_SHARED_S_MAX_D 64
 #endif
+// FA_FAST_SOFTMAX / FA_FAST_MIN_D - the fast softmax path (see kFastSumLimit) for head dims >= FA_FAST_MIN_D (default 128).
+#ifndef FA_FAST_SOFTMAX
+#define FA_FAST_SOFTMAX 1
+#endif
 #ifndef FA_FAST_MIN_D
 #define FA_FAST_MIN_D 128
 #endif
-// 1: the MMA warp polls its barriers with mbarrier.test_wait in a tight loop instead of the suspending try_wait
-// 1: the epilogue warpgroup's item-long wait for 1/l is a named barrier (no polling) instead of an mbarrier
+// FA_UNIFORM_HINT - warp index and work-item ids pass through __shfl_sync(.., 0), which tells the compiler they are
+//   warp-uniform: item state, TMEM / barrier addresses and UMMA descriptor arithmetic then live in uniform registers
+//   instead of being recomputed from threadIdx after every barrier wait (c3 on zero inputs 1616 -> 1719 TFLOP/s, no spill
+//   left in the 40-register issuer warp).
+#ifndef FA_UNIFORM_HINT
+#define FA_UNIFORM_HINT 1
+#endif
+// FA_EP_NAMED_BAR - the epilogue warpgroup's item-long wait for 1/l is a hardware named barrier (no polling) instead of
+//   an mbarrier (+0.3 %).
 #ifndef FA_EP_NAMED_BAR
 #define FA_EP_NAMED_BAR 1
 #endif
+// FA_MMA_SPIN - the MMA warp polls its barriers with mbarrier.test_wait in a tight loop instead of the suspending
+//   try_wait.  Measured 5 % slower (the poll steals issue slots from the softmax warps of its SMSP); default 0.
 #ifndef FA_MMA_SPIN
 #define FA_MMA_SPIN 0
 #endif
-#ifndef FA_FAST_SOFTMAX
-#define FA_FAST_SOFTMAX 1
+// FA_TWO_ISSUERS - TWO MMA issuer warps, one per Q tile (warps 13 and 15), each walking only its own tile's chain (S_i ->
+//   softmax -> P_i V -> Q_i K^T) so that a wait for the other tile's P never holds up this tile's MMAs and nothing is
+//   serialised at a work-item boundary; K/V stages are released by two arrivals (an issuer that does not use a stage
+//   arrives for it after seeing it filled); d <= 64 TMEM map S0 | S1 | P0 | P1 | O0 | O1.  Correct (parity list green) but
+//   MEASURED MUCH SLOWER at d = 128: c3 on zero inputs 1615 -> 1168 TFLOP/s (the same on random inputs), c2 523 -> 485,
+//   d = 64 long sequences unchanged (873 -> 869): MMAs of two issuing threads interleave on the tensor pipe, and every
+//   switch between accumulator tiles costs what a fixed order pays only four times per step.  Default 0: one issuer
+//   (warp 13) for both tiles, fixed interleaved order (profiles/r02_fast_softmax_ab.log).
+#ifndef FA_TWO_ISSUERS
+#define FA_TWO_ISSUERS 0
 #endif
 
 template <int D>
